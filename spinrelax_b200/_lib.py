@@ -1,0 +1,80 @@
+"""ctypes binding of libspinrelax_b200.so (the C ABI in include/spinrelax_b200.h).
+
+There is no CPU fallback: if the library is missing it is built with nvcc, and if that fails or no
+CUDA device is present every compute call raises.
+"""
+import ctypes
+import os
+
+from . import build as _build
+
+_c = ctypes
+_LIB = None
+
+
+class SpinRelaxError(RuntimeError):
+    pass
+
+
+def _declare(lib):
+    ll, i, vp, sz = _c.c_longlong, _c.c_int, _c.c_void_p, _c.c_size_t
+    dp = _c.POINTER(_c.c_double)
+    sig = {
+        "sr_abi_version": (i, []),
+        "sr_last_error": (_c.c_char_p, []),
+        "sr_device_info": (i, [_c.POINTER(i), _c.POINTER(i), _c.POINTER(i), _c.POINTER(sz)]),
+        "sr_ct_row_pitch": (ll, [ll]),
+        "sr_ct_workspace_bytes": (sz, [i, ll, i]),
+        "sr_pack_vectors_f32": (i, [vp, i, ll, i, dp, vp, ll, vp]),
+        "sr_ct_lag_sums": (i, [vp, ll, i, ll, i, ll, vp, vp]),
+        "sr_ct_palmer_finalize": (i, [vp, i, ll, i, ll, vp, vp, vp]),
+        "sr_ct_palmer_device": (i, [vp, i, ll, i, vp, vp, vp, sz, vp]),
+        "sr_ct_palmer_host": (i, [vp, i, ll, i, vp, vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    return sig
+
+
+def lib_path():
+    return _build.LIB
+
+
+def load():
+    """Load (building first if needed) the shared library. Raises if it cannot be produced."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = _build.LIB
+    if not os.path.exists(path):
+        _build.build()
+    lib = _c.CDLL(path)
+    _declare(lib)
+    if lib.sr_abi_version() != 1:
+        raise SpinRelaxError("libspinrelax_b200.so ABI version mismatch")
+    _LIB = lib
+    return lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = load().sr_last_error().decode("utf-8", "replace")
+        raise SpinRelaxError("%s failed (%d): %s" % (what or "libspinrelax_b200 call", rc, msg))
+
+
+def require_cuda():
+    import torch
+
+    if not torch.cuda.is_available():
+        raise SpinRelaxError(
+            "spinrelax_b200 needs a CUDA device (sm_100a); there is no CPU fallback for this path"
+        )
+    return torch
+
+
+def current_stream_ptr():
+    import torch
+
+    return _c.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -1,0 +1,119 @@
+"""Host mirror of the C(t) functions of calculate-Ct-from-traj.py, backed by the CUDA path.
+
+Same names, argument meaning and return layout as the reference:
+  calculate_Ct_Palmer   calculate-Ct-from-traj.py:200-238
+  reformat_vecs_by_tau  calculate-Ct-from-traj.py:245-275
+  calculate_dt          calculate-Ct-from-traj.py:240-243
+All numerics run in libspinrelax_b200.so (sr_ct_palmer_*); nothing here computes C(t) on the CPU.
+"""
+import ctypes
+import sys
+
+import numpy as np
+
+from . import _lib
+
+
+def calculate_dt(dt, tau):
+    """Time axis of the C(t) points (calculate-Ct-from-traj.py:240-243): (1..int(0.5*tau/dt)) * dt."""
+    nPts = int(0.5 * tau / dt)
+    return (np.arange(nPts) + 1.0) * dt
+
+
+def reformat_vecs_by_tau(vecs, dt, tau):
+    """Cut every trajectory to a whole number of tau-long chunks and stack them.
+
+    vecs: list (or array) of per-file arrays (frames, bonds, 3); frame counts may differ between files
+    (the reference's own np.array(list) at :498 cannot hold ragged input on NumPy >= 1.24, the function
+    at :245-275 can).  Returns (nChunk, int(tau/dt), bonds, 3) with the dtype of the first file.
+    """
+    nFiles = len(vecs)
+    nFramesPerChunk = int(tau / dt)
+    if nFramesPerChunk < 1:
+        raise ValueError("reformat_vecs_by_tau: tau/dt < 1 frame per chunk")
+    used = [int(v.shape[0] / nFramesPerChunk) * nFramesPerChunk for v in vecs]
+    nFramesTot = int(sum(used))
+    first = vecs[0]
+    out = np.zeros((nFramesTot, first.shape[1], first.shape[2]), dtype=first.dtype)
+    start = 0
+    for i in range(nFiles):
+        end = start + used[i]
+        out[start:end] = vecs[i][: used[i]]
+        start = end
+    return out.reshape((nFramesTot // nFramesPerChunk, nFramesPerChunk, first.shape[1], first.shape[2]))
+
+
+def _check_4d(vecs):
+    sh = vecs.shape
+    if len(sh) != 4 or sh[-1] != 3:
+        # reference: message to stderr + sys.exit(1) (calculate-Ct-from-traj.py:213-216)
+        print("= = = ERROR: The input vectors to calculate_Ct_Palmer is not of the expected "
+              "4-dimensional form! %s" % (sh,), file=sys.stderr)
+        sys.exit(1)
+    if sh[1] < 50:
+        print("= = = WARNING: there are less than 50 frames per block of memory-time!", file=sys.stderr)
+    return sh
+
+
+def ct_palmer_device(vecs, workspace=None, return_workspace=False):
+    """C(t), dC(t) from a CUDA float32 tensor (nC, nF, nR, 3). Returns two (nF//2, nR) float32 tensors."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    if not (vecs.is_cuda and vecs.dtype == torch.float32 and vecs.is_contiguous()):
+        raise _lib.SpinRelaxError("ct_palmer_device: need a contiguous float32 CUDA tensor")
+    nC, nF, nR, _ = _check_4d(vecs)
+    L = nF // 2
+    need = lib.sr_ct_workspace_bytes(nC, nF, nR)
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty(need, dtype=torch.uint8, device=vecs.device)
+    Ct = torch.empty((L, nR), dtype=torch.float32, device=vecs.device)
+    dCt = torch.empty((L, nR), dtype=torch.float32, device=vecs.device)
+    rc = lib.sr_ct_palmer_device(vecs.data_ptr(), nC, nF, nR, Ct.data_ptr(), dCt.data_ptr(),
+                                 workspace.data_ptr(), workspace.numel(), _lib.current_stream_ptr())
+    _lib.check(rc, "sr_ct_palmer_device")
+    if return_workspace:
+        return Ct, dCt, workspace
+    return Ct, dCt
+
+
+def ct_lag_sums_device(vecs):
+    """Raw FP64 lag sums S[nR, nC, L] = sum_t (u(t).u(t+delta))^2 (test / diagnostics entry)."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    nC, nF, nR, _ = _check_4d(vecs)
+    L = nF // 2
+    pitch = lib.sr_ct_row_pitch(nF)
+    packed = torch.empty((nR, nC, pitch, 4), dtype=torch.float32, device=vecs.device)
+    S = torch.empty((nR, nC, L), dtype=torch.float64, device=vecs.device)
+    st = _lib.current_stream_ptr()
+    _lib.check(lib.sr_pack_vectors_f32(vecs.data_ptr(), nC, nF, nR, None, packed.data_ptr(), pitch, st),
+               "sr_pack_vectors_f32")
+    _lib.check(lib.sr_ct_lag_sums(packed.data_ptr(), pitch, nC, nF, nR, L, S.data_ptr(), st), "sr_ct_lag_sums")
+    return S
+
+
+def calculate_Ct_Palmer(vecs):
+    """Drop-in for calculate_Ct_Palmer (calculate-Ct-from-traj.py:200-238).
+
+    vecs: (nReplicates, nFrames, nResidues, 3) array.  Returns (Ct, dCt), each (nFrames//2, nResidues)
+    with vecs' dtype; first row is delta = 1.  Input is taken through the host-buffer C ABI
+    (sr_ct_palmer_host): H2D, CUDA kernels, D2H.  float64 input is computed from its float32 rounding
+    (the reference's own pipeline only ever produces float32 vectors, obtain_XHvecs :64-86).
+    """
+    _lib.require_cuda()
+    lib = _lib.load()
+    vecs = np.asarray(vecs)
+    sh = _check_4d(vecs)
+    print("= = = Debug of calculate_Ct_Palmer confirming the dimensions of vecs:", sh)
+    out_dtype = vecs.dtype if vecs.dtype in (np.float32, np.float64) else np.float32
+    v32 = np.ascontiguousarray(vecs, dtype=np.float32)
+    nC, nF, nR, _ = sh
+    L = int(nF / 2)
+    Ct = np.empty((L, nR), dtype=np.float32)
+    dCt = np.empty((L, nR), dtype=np.float32)
+    if L == 0:
+        return Ct.astype(out_dtype), dCt.astype(out_dtype)
+    rc = lib.sr_ct_palmer_host(v32.ctypes.data_as(ctypes.c_void_p), nC, nF, nR,
+                               Ct.ctypes.data_as(ctypes.c_void_p), dCt.ctypes.data_as(ctypes.c_void_p))
+    _lib.check(rc, "sr_ct_palmer_host")
+    return Ct.astype(out_dtype, copy=False), dCt.astype(out_dtype, copy=False)
