@@ -1,0 +1,295 @@
+#!/usr/bin/env python
+"""Headline benchmark: C(t) bond-vector x frame x lag pairs/s on BASELINE config 2
+(76 N-H vectors, 10^6 frames = 5 chunks x 2e5, max lag 1e5, + PAF rotation and spherical histogram).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One step = one pass of the hot path over the batch: K2 pack -> K1 lag sums -> Palmer finalize
+(-> K3 rotation + histogram).  `value` is timed with inputs resident in HBM, `e2e` goes through the
+public host-buffer call (pinned host input, H2D, kernels, D2H).  N > 1: one process per GPU (torchrun),
+every rank owns its own shard of bond vectors (weak scaling, no data-path collective; the (L, nR)
+result rows are gathered to rank 0 inside the timed region).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# workload = BASELINE.json configs[1]
+N_VEC, N_CHUNK, N_FRAMES_PER_CHUNK = 76, 5, 200000
+Q_PAF = (0.83, -0.31, 0.22, 0.41)
+METRIC = "ct_pairs_per_s"
+UNIT = "bond-vector*frame*lag pairs/s"
+
+
+def n_pairs(nR, nC, nF, L):
+    return nR * nC * (L * nF - L * (L + 1) // 2)
+
+
+def workload_config(n_gpus):
+    return {"workload": "BASELINE config 2: %d N-H vectors x 1e6 frames (%d chunks x %d), max lag %d, "
+                        "C(t) Palmer + PAF rotation + 72x36 vecHistogram" % (N_VEC, N_CHUNK, N_FRAMES_PER_CHUNK,
+                                                                             N_FRAMES_PER_CHUNK // 2),
+            "n_vectors_per_gpu": N_VEC, "n_chunks": N_CHUNK, "frames_per_chunk": N_FRAMES_PER_CHUNK,
+            "max_lag": N_FRAMES_PER_CHUNK // 2, "sharding": "bond vectors, %d per rank" % N_VEC,
+            "l2": "inputs (0.9 GB AoS, 1.2 GB packed) exceed the 126 MB L2; no flush needed",
+            "pairs_per_step_per_gpu": n_pairs(N_VEC, N_CHUNK, N_FRAMES_PER_CHUNK, N_FRAMES_PER_CHUNK // 2)}
+
+
+def make_input(rank):
+    from spinrelax_b200 import synth
+    v = synth.nh_vectors(N_CHUNK * N_FRAMES_PER_CHUNK, N_VEC, seed=synth.BASE_SEED + 2 + 1000 * rank)
+    return v.reshape(N_CHUNK, N_FRAMES_PER_CHUNK, N_VEC, 3)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, val in zip(names, r[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(n)
+        busy = [x for x in sm if x > 0.5 * max(mx)] or sm
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    p = {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0, "source": "fallback (B200_PROFILING.md)"}
+    if os.path.exists(path):
+        with open(path) as fp:
+            m = json.load(fp)
+        p = {"hbm_gbs": m.get("hbm_gbs", 6650.0), "sm_max_mhz": m.get("sm_max_mhz", 1965.0),
+             "source": "MEASURED_PEAKS.json"}
+    # FP32 CUDA-core FMA peak is not in MEASURED_PEAKS.json: 148 SM x 128 lanes x 2 flop x measured max SM clock
+    p["fp32_tflops"] = 148 * 128 * 2 * p["sm_max_mhz"] * 1e6 / 1e12
+    return p
+
+
+# =====================================================================================================
+# reference arm: the reference's own CPU implementation of the path (NumPy einsum per lag,
+# calculate-Ct-from-traj.py:222-228) via the oracle port, on all host cores, bounded lag sample per step
+# =====================================================================================================
+_REF_V = None
+
+
+def _ref_task(args):
+    lag, r0, r1 = args
+    from oracle import ct_oracle
+    ct_oracle.ct_lag_body(_REF_V[:, :, r0:r1], lag)
+    nC, nF = _REF_V.shape[0], _REF_V.shape[1]
+    return nC * (nF - lag) * (r1 - r0)
+
+
+def sample_lags(n):
+    L = N_FRAMES_PER_CHUNK // 2
+    return sorted(set(int(x) for x in np.unique(np.round(np.linspace(1, L, n)))))
+
+
+def run_reference(args):
+    global _REF_V
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = min(os.cpu_count() or 1, 32)
+    _REF_V = make_input(0)
+    lags = sample_lags(max(2, cores // 2))
+    blocks = [(0, 19), (19, 38), (38, 57), (57, 76)]
+    tasks = [(lag, a, b) for lag in lags for (a, b) in blocks]
+    ctx = mp.get_context("fork")
+    times, pairs = [], 0
+    with ctx.Pool(cores) as pool:
+        for it in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            pairs = sum(pool.map(_ref_task, tasks, chunksize=1))
+            dt = time.perf_counter() - t0
+            if it >= args.warmup:
+                times.append(dt)
+    total = sum(times)
+    value = pairs * len(times) / total
+    sample = ("oracle port of the per-lag body (calculate-Ct-from-traj.py:223-228) on the full config-2 array, "
+              "%d lags spread over 1..1e5 x 4 vector blocks per step, %d worker processes" % (len(lags), cores))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(args.gpus),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def cpu_baseline_single(v4):
+    """Reference path, single thread as shipped: exact per-lag body on a bounded lag sample (~10-20 s)."""
+    from oracle import ct_oracle
+    lags = sample_lags(12)
+    t0 = time.perf_counter()
+    pairs = 0
+    for lag in lags:
+        ct_oracle.ct_lag_body(v4, lag)
+        pairs += v4.shape[0] * (v4.shape[1] - lag) * v4.shape[2]
+        if time.perf_counter() - t0 > 25.0:
+            break
+    dt = time.perf_counter() - t0
+    return {"value": pairs / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": "oracle.ct_oracle.ct_lag_body (calculate-Ct-from-traj.py:223-228) on the full config-2 "
+                      "float32 array for lags %s; %.1f s" % (lags[:len(lags)], dt),
+            "host_cores": os.cpu_count()}
+
+
+# =====================================================================================================
+# our arm
+# =====================================================================================================
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from spinrelax_b200 import _lib, ct, pipeline
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    lib = _lib.load()
+
+    v_host = torch.from_numpy(make_input(rank)).pin_memory()
+    nC, nF, nR = N_CHUNK, N_FRAMES_PER_CHUNK, N_VEC
+    L = nF // 2
+    v_dev = v_host.to(dev, non_blocking=True)
+    torch.cuda.synchronize()
+    step = pipeline.CtHistStep(nC, nF, nR, q_rot=Q_PAF, device=dev, world=world, rank=rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing -------------------------------------------------------------------
+    for _ in range(args.warmup):
+        step.run_device(v_dev)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    step.reset_kernel_timers()
+    e0.record()
+    for _ in range(args.steps):
+        step.run_device(v_dev, time_kernels=True)
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    kt = step.kernel_times_ms()           # per-kernel average launch duration (CUDA events on the launch stream)
+
+    # ---- end to end through the public host API ------------------------------------------------------
+    v_np = v_host.numpy()
+    for _ in range(min(args.warmup, 1)):
+        step.run_host(v_np)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, 3))
+    for _ in range(e2e_steps):
+        out = step.run_host(v_np)
+    barrier()
+    e2e_s = (time.perf_counter() - t0)
+
+    t = torch.tensor([ms_total, e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, e2e_s = float(t[0]), float(t[1])
+
+    if rank == 0:
+        pairs_gpu = n_pairs(nR, nC, nF, L)
+        value = pairs_gpu * world * args.steps / (ms_total * 1e-3)
+        pk = peaks()
+        lag_ms = kt["ct_lag_kernel"]
+        achieved = pairs_gpu * 7 / (lag_ms * 1e-3) / 1e12
+        roof = {"kernel": "ct_lag_kernel", "bound": "fp32", "achieved": achieved, "peak": pk["fp32_tflops"],
+                "unit": "TFLOP/s", "frac": achieved / pk["fp32_tflops"], "traffic": step.ncu_traffic_bytes(),
+                "flop_per_pair": 7, "peak_source": "148 SM x 128 FP32 lanes x 2 x sm_max_mhz (%s); FP32 CUDA-core "
+                "peak is not in MEASURED_PEAKS.json, measured FFMA microbenchmark = 72.5 TFLOP/s "
+                "(profiles/r01_microbench_b200.jsonl)" % pk["source"],
+                "share_of_step": lag_ms / (ms_total / args.steps), "kernel_ms": kt}
+        if "sphere_hist_kernel" in kt:
+            samples = nC * nF * nR
+            gbs = samples * 12 / (kt["sphere_hist_kernel"] * 1e-3) / 1e9
+            roof["streaming"] = {"kernel": "sphere_hist_kernel", "bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"],
+                                 "unit": "GB/s", "frac": gbs / pk["hbm_gbs"], "bytes_per_sample": 12}
+        cpu = cpu_baseline_single(v_np) if world == 1 else None
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32 products, f64 accumulation",
+                "data": "synthetic", "config": workload_config(world), "clocks": clocks,
+                "e2e": {"value": pairs_gpu * world * e2e_steps / e2e_s, "unit": UNIT,
+                        "h2d_bytes_per_step": int(v_np.nbytes), "d2h_bytes_per_step": int(step.d2h_bytes()),
+                        "steps": e2e_steps, "api": "spinrelax_b200.pipeline.CtHistStep.run_host (sr_ct_palmer_host "
+                        "+ sr_sphere_hist_host through the C ABI)"},
+                "gpu_launches": step.launches_per_step() * args.steps, "roofline": roof, "cpu_baseline": cpu}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

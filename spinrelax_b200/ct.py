@@ -92,7 +92,12 @@ def ct_lag_sums_device(vecs):
     return S
 
 
-def calculate_Ct_Palmer(vecs):
+def calculate_Ct_Palmer_quiet(vecs):
+    """calculate_Ct_Palmer without the reference's debug print."""
+    return calculate_Ct_Palmer(vecs, _verbose=False)
+
+
+def calculate_Ct_Palmer(vecs, _verbose=True):
     """Drop-in for calculate_Ct_Palmer (calculate-Ct-from-traj.py:200-238).
 
     vecs: (nReplicates, nFrames, nResidues, 3) array.  Returns (Ct, dCt), each (nFrames//2, nResidues)
@@ -100,11 +105,12 @@ def calculate_Ct_Palmer(vecs):
     (sr_ct_palmer_host): H2D, CUDA kernels, D2H.  float64 input is computed from its float32 rounding
     (the reference's own pipeline only ever produces float32 vectors, obtain_XHvecs :64-86).
     """
-    _lib.require_cuda()
-    lib = _lib.load()
     vecs = np.asarray(vecs)
     sh = _check_4d(vecs)
-    print("= = = Debug of calculate_Ct_Palmer confirming the dimensions of vecs:", sh)
+    _lib.require_cuda()
+    lib = _lib.load()
+    if _verbose:
+        print("= = = Debug of calculate_Ct_Palmer confirming the dimensions of vecs:", sh)
     out_dtype = vecs.dtype if vecs.dtype in (np.float32, np.float64) else np.float32
     v32 = np.ascontiguousarray(vecs, dtype=np.float32)
     nC, nF, nR, _ = sh

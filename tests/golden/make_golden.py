@@ -1,0 +1,288 @@
+"""Generate the committed golden vectors by running the REAL SpinRelax code (build container only).
+
+    python tests/golden/make_golden.py
+
+Needs /root/reference and oracle/_ref/npufunc (cd oracle && make).  Inputs are seeded synthetic data
+from spinrelax_b200.synth; inputs small enough are stored next to the reference outputs so the tests
+never depend on regenerating them bit-for-bit.  The reference has no tests or fixtures of its own
+(SURVEY.md section 4), so these files are the pin for oracle/ and for the CUDA path.
+"""
+import contextlib
+import io
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import ref_loader  # noqa: E402
+from spinrelax_b200 import synth  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+@contextlib.contextmanager
+def quiet():
+    with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+        yield
+
+
+def save(name, **arrs):
+    path = os.path.join(OUT, name)
+    np.savez_compressed(path, **arrs)
+    print("%-28s %8.1f kB" % (name, os.path.getsize(path) / 1e3))
+
+
+def golden_ct(refct):
+    # small, ragged-friendly case: 2 trajectories with different frame counts -> reformat -> C(t)
+    trajs = [synth.nh_vectors(1130, 6, seed=synth.BASE_SEED + 1), synth.nh_vectors(877, 6, seed=synth.BASE_SEED + 2)]
+    with quiet():
+        v4 = refct.reformat_vecs_by_tau(trajs, 10.0, 2000.0)          # -> (9, 200, 6, 3)
+        Ct32, dCt32 = refct.calculate_Ct_Palmer(v4)
+        Ct64, dCt64 = refct.calculate_Ct_Palmer(v4.astype(np.float64))
+        dt = refct.calculate_dt(10.0, 2000.0)
+    save("ct_small.npz", traj0=trajs[0], traj1=trajs[1], vecs=v4, Ct32=Ct32, dCt32=dCt32, Ct64=Ct64, dCt64=dCt64,
+         dt=dt)
+    # BASELINE config 1 shape (76 vectors, 10 chunks x 1000 frames); input regenerated from the seed,
+    # outputs stored for a lag subset to stay small, plus a checksum of the input
+    v = synth.nh_vectors(10000, 76, seed=synth.BASE_SEED + 11)
+    with quiet():
+        v4 = refct.reformat_vecs_by_tau([v], 10.0, 10000.0)
+        Ct64, dCt64 = refct.calculate_Ct_Palmer(v4.astype(np.float64))
+        Ct32, dCt32 = refct.calculate_Ct_Palmer(v4)
+    lags = np.unique(np.concatenate((np.arange(1, 33), np.arange(40, 500, 23), [479, 480, 481, 499, 500])))
+    save("ct_config1.npz", seed=synth.BASE_SEED + 11, shape=np.array(v4.shape), lags=lags,
+         input_sum=np.float64(v.astype(np.float64).sum()), input_head=v[:4],
+         Ct64=Ct64[lags - 1], dCt64=dCt64[lags - 1], Ct32=Ct32[lags - 1], dCt32=dCt32[lags - 1])
+    # known-answer inputs: static vectors, single chunk (dCt = 0/0), odd frame count
+    stat = np.repeat(synth.nh_vectors(1, 3, seed=5)[None], 60, axis=1).reshape(1, 60, 3, 3).repeat(2, axis=0)
+    one = synth.nh_vectors(101, 2, seed=9).reshape(1, 101, 2, 3)
+    with quiet(), np.errstate(all="ignore"):
+        a = refct.calculate_Ct_Palmer(stat.astype(np.float64))
+        b = refct.calculate_Ct_Palmer(one.astype(np.float64))
+    save("ct_edge.npz", static=stat, static_Ct=a[0], static_dCt=a[1], one=one, one_Ct=b[0], one_dCt=b[1])
+
+
+def _away_from_edges(v, q, nbx, margin):
+    """Drop samples whose phi or cos(theta) lies within `margin` of a bin edge, so that the committed
+    counts do not depend on the last ulp of the host libm (arctan2/arccos/cos differ between CPUs)."""
+    qs = ref_loader.module("transforms3d_supplement")
+    gm = ref_loader.module("general_maths")
+    w = qs.rotate_vector_simd(v, q) if q is not None else v
+    rtp = gm.xyz_to_rtp(w.astype(np.float64))
+    phi, cth = rtp[..., 1], np.cos(rtp[..., 2])
+    ephi = np.linspace(-np.pi, np.pi, nbx + 1)
+    ecth = np.linspace(-1, 1, nbx // 2 + 1)
+    dphi = np.min(np.abs(phi[..., None] - ephi), axis=-1)
+    dcth = np.min(np.abs(cth[..., None] - ecth), axis=-1)
+    ok = np.all((dphi > margin) & (dcth > margin), axis=1)
+    return v[ok]
+
+
+def golden_hist(refct):
+    qs = ref_loader.module("transforms3d_supplement")
+    gm = ref_loader.module("general_maths")
+    q = np.array([0.83, -0.31, 0.22, 0.41])
+    q = q / np.linalg.norm(q)
+    v = synth.nh_vectors(6000, 7, seed=synth.BASE_SEED + 21)
+    # add exact on-axis / on-edge samples: +z, -z, +x, -x, +y, and a zero vector (NaN -> dropped)
+    special = np.zeros((6, 7, 3), dtype=np.float32)
+    special[0, :, 2] = 1; special[1, :, 2] = -1; special[2, :, 0] = 1; special[3, :, 0] = -1; special[4, :, 1] = 1
+
+    def run(vecs, quat, nbx):
+        with np.errstate(all="ignore"):
+            w = qs.rotate_vector_simd(vecs, quat) if quat is not None else vecs          # :567
+            rtp = gm.xyz_to_rtp(w)                                                      # :588
+            rtp = np.transpose(rtp, axes=(1, 0, 2))                                     # :600
+            rtp = np.delete(rtp, 0, axis=2)                                             # :611
+            rtp[..., 1] = np.cos(rtp[..., 1])                                           # :613
+            hl = np.zeros((vecs.shape[1], nbx, nbx // 2), dtype=rtp.dtype)
+            for i in range(vecs.shape[1]):                                              # :617-626 (no `normed`)
+                h, e = np.histogramdd(rtp[i], bins=(nbx, nbx // 2), range=((-np.pi, np.pi), (-1, 1)))
+                hl[i] = h
+        return hl, e
+
+    vr = _away_from_edges(v, q, 72, 1e-9)
+    h_rot, e = run(vr, q, 72)
+    v32 = _away_from_edges(v, None, 72, 2e-5)
+    h_f32, _ = run(v32, None, 72)
+    h_special, _ = run(special, None, 72)          # identity-frame on-edge semantics (float32 path)
+    vr36 = _away_from_edges(v, q, 36, 1e-9)
+    h_rot36, e36 = run(vr36, q, 36)
+    save("hist.npz", q=q, vecs_rot=vr, hist_rot=h_rot.astype(np.int64), edges_phi=e[0], edges_cos=e[1],
+         vecs_f32=v32, hist_f32=h_f32.astype(np.int64), special=special, hist_special=h_special.astype(np.int64),
+         vecs_rot36=vr36, hist_rot36=h_rot36.astype(np.int64))
+    # S2 and average vector of the same stream (next-tier rows, same pass)
+    with quiet():
+        s2 = refct.calculate_S2_by_outerProduct(vr.astype(np.float64)[:5000], 10.0, 10000.0)
+        s2_all = refct.calculate_S2_by_outerProduct(vr.astype(np.float64))
+    save("s2.npz", vecs=vr[:5000], s2_blocks=s2, s2_all=s2_all)
+
+
+def golden_dq(refdq):
+    q = synth.quaternion_walk(6000, seed=synth.BASE_SEED + 31, sigma=(0.01, 0.015, 0.03))     # float32 (G2)
+    lags = [5, 10, 40, 100, 333, 1000, 2999]
+    nch = 4
+    rec = dict(vxx=[], iso=[], moi=[], chunk_iso=[], chunk_moi=[], moi_rot=[], chunk_moi_rot=[])
+    qf = np.array([0.9, 0.1, -0.3, 0.2]); qf = qf / np.linalg.norm(qf)
+    for d in lags:
+        dq = refdq.obtain_self_dq(q, d)
+        v = dq[..., 1:4]
+        n = len(v)
+        rec["iso"].append(refdq.average_LegendreP1quat(n, v))
+        rec["moi"].append(refdq.average_anisotropic_tensor(n, v))
+        rec["moi_rot"].append(refdq.average_anisotropic_tensor(n, v, qf))
+        rec["chunk_iso"].append(refdq.average_LegendreP1quat_chunk(n, v, nch))
+        rec["chunk_moi"].append(refdq.average_anisotropic_tensor_chunk(n, v, nch))
+        rec["chunk_moi_rot"].append(refdq.average_anisotropic_tensor_chunk(n, v, nch, qf))
+    dq5 = refdq.obtain_self_dq(q, 5)
+    save("dq_moments.npz", q=q, lags=np.array(lags), nchunk=nch, qframe=qf, dq_lag5=dq5,
+         **{k: np.array(val) for k, val in rec.items() if val})
+    # end-to-end CLI on a PLUMED text file (run-all.bash:379-387 flags), outputs stored as text
+    import subprocess
+    import tempfile
+    with tempfile.TemporaryDirectory() as td:
+        qq = synth.quaternion_walk(20000, seed=synth.BASE_SEED + 32, sigma=(0.004, 0.006, 0.012), dtype=np.float64)
+        fn = os.path.join(td, "colvar-q")
+        synth.write_plumed_quaternions(fn, qq, dt=10.0)
+        env = dict(os.environ, PYTHONPATH=os.pathsep.join([ref_loader.STUBS, ref_loader.REF_BUILD, ref_loader.REFERENCE]))
+        cmd = [sys.executable, os.path.join(ref_loader.REFERENCE, "calculate-dq-distribution.py"), "--iso", "--aniso",
+               "-f", fn, "-o", os.path.join(td, "rotdif"), "--mindt", "500", "--skip", "500", "--maxdt", "50000",
+               "--num_chunk", "4"]
+        subprocess.run(cmd, env=env, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, cwd=td)
+        files = {}
+        for suf in ("-iso.dat", "-aniso2.dat", "-aniso_q.dat", "-moi.xyz"):
+            with open(os.path.join(td, "rotdif" + suf)) as fp:
+                files[suf] = fp.read()
+        with open(fn) as fp:
+            plumed = fp.read()
+    save("dq_cli.npz", plumed=np.array(plumed), iso=np.array(files["-iso.dat"]), aniso2=np.array(files["-aniso2.dat"]),
+         aniso_q=np.array(files["-aniso_q.dat"]), moi_xyz=np.array(files["-moi.xyz"]))
+
+
+def _synthetic_curves(n_res, n_pts, seed):
+    rng = np.random.default_rng(seed)
+    t = (np.arange(n_pts) + 1.0) * 10.0
+    Ct, dCt, truth = [], [], []
+    for i in range(n_res):
+        S2 = rng.uniform(0.45, 0.9)
+        nc = 1 + i % 3
+        C = rng.dirichlet(np.ones(nc)) * (1 - S2) * rng.uniform(0.85, 1.0)
+        tau = np.sort(10 ** rng.uniform(1.2, 3.2, nc))
+        y = S2 + np.sum(C[:, None] * np.exp(-t[None] / tau[:, None]), axis=0)
+        sig = 0.002 + 0.004 * t / t[-1]
+        y = y + rng.standard_normal(n_pts) * sig * 0.5
+        Ct.append(y); dCt.append(sig); truth.append((S2, C, tau))
+    return t, np.array(Ct), np.array(dCt), truth
+
+
+def golden_fit():
+    fitCt = ref_loader.module("fitting_Ct_functions")
+    t, Ct, dCt, _ = _synthetic_curves(9, 250, synth.BASE_SEED + 41)
+    rows = []
+    single = []
+    for i in range(len(Ct)):
+        m = fitCt.autoCorrelationModel(name=i)
+        with quiet():
+            chi = m.optimised_curve_fitting(t, Ct[i], dCt[i], listDoG=[2, 3, 5, 7, 9], chiSqThreshold=0.5,
+                                            fp=io.StringIO())
+        p = np.full(12, np.nan)
+        p[0] = m.nParams; p[1] = chi; p[2] = m.S2
+        p[3:3 + m.nComps] = m.C; p[7:7 + m.nComps] = m.tau
+        rows.append(p)
+        for npar in (2, 3, 5):
+            m2 = fitCt.autoCorrelationModel(name=i)
+            m2.set_nParams(npar)
+            with quiet():
+                chi2, qual = m2.conduct_curve_fitting(t, Ct[i], dCt[i], bReInitialise=True, fp=io.StringIO())
+            r = np.full(16, np.nan)
+            r[0] = npar; r[1] = chi2; r[2:5] = qual; r[5] = m2.S2
+            if np.isfinite(chi2):
+                r[6:6 + m2.nComps] = m2.C; r[9:9 + m2.nComps] = m2.tau
+                r[12:12 + m2.nComps] = m2.dC
+            single.append(r)
+    save("fit.npz", t=t, Ct=Ct, dCt=dCt, ladder=np.array(rows), single=np.array(single))
+
+
+def golden_relax():
+    sd = ref_loader.module("spectral_densities")
+    fitCt = ref_loader.module("fitting_Ct_functions")
+    npufunc = ref_loader.module("npufunc")
+    rng = np.random.default_rng(synth.BASE_SEED + 51)
+    nR = 6
+    # histogram weights: counts of a synthetic rotated stream
+    q = np.array([0.83, -0.31, 0.22, 0.41]); q = q / np.linalg.norm(q)
+    v = synth.nh_vectors(3000, nR, seed=synth.BASE_SEED + 52)
+    from oracle import ct_oracle
+    hist, edges = ct_oracle.sphere_histogram(v, q)
+    import tempfile
+    models = fitCt.autoCorrelations()
+    pars = []
+    for i in range(nR):
+        nc = 1 + i % 3
+        S2 = rng.uniform(0.5, 0.9)
+        C = rng.dirichlet(np.ones(nc)) * (1 - S2)
+        tau = np.sort(10 ** rng.uniform(1.0, 3.3, nc))
+        models.add_model(str(i), name=i, listC=list(C), listTau=list(tau), S2=S2, bS2Fast=False)
+        row = np.full(8, np.nan); row[0] = nc; row[1] = S2; row[2:2 + nc] = C; row[5:5 + nc] = tau
+        pars.append(row)
+    zeta = (1.02 / 1.04) ** 6
+    models.set_zeta(zeta)
+    res = {}
+    with tempfile.TemporaryDirectory() as td:
+        fn = os.path.join(td, "h_vecHistogram.npz")
+        e_obj = np.empty(2, dtype=object); e_obj[0] = edges[0]; e_obj[1] = edges[1]
+        np.savez_compressed(fn, names=np.arange(nR), dataType="LambertCylindrical", bHistogram=True, edges=e_obj,
+                            axisLabels=["phi", "cos(theta)"], data=hist)
+        for tag, Dani in (("prolate", 1.35), ("oblate", 0.8)):
+            with quiet():
+                rot = sd.globalRotationalDiffusion_Axisymmetric(D=[2.1e-5, Dani], bConvert=False)
+                rot.import_frame_vectors(fn)
+            for field in (600.133, 800.0):
+                with quiet():
+                    w = sd.angularFrequencies("15N", "1H", field, "MHz", "ps")
+                    for name, cls in (("R1", sd.spinRelaxationR1), ("R2", sd.spinRelaxationR2), ("NOE", sd.spinRelaxationNOE)):
+                        ex = cls(name, "ps", w, rot, models)
+                        ex.eval()
+                        res["%s_%s_%d" % (tag, name, round(field))] = np.stack((ex.values, ex.errors))
+        with quiet():
+            iso = sd.globalRotationalDiffusion_Isotropic(D=2.1e-5)
+            w = sd.angularFrequencies("15N", "1H", 600.133, "MHz", "ps")
+            for name, cls in (("R1", sd.spinRelaxationR1), ("R2", sd.spinRelaxationR2), ("NOE", sd.spinRelaxationNOE)):
+                ex = cls(name, "ps", w, iso, models)
+                ex.eval()
+                res["iso_%s_600" % name] = np.array(ex.values)
+            # per-residue CSA array path (the rsCSA grid workload): eval(ind=i) with a CSA array
+            w2 = sd.angularFrequencies("15N", "1H", 600.133, "MHz", "ps")
+            csa = -170e-6 + 10e-6 * np.arange(nR)
+            w2.initialise_CSA_array(nR, csa)
+            rotp = sd.globalRotationalDiffusion_Axisymmetric(D=[2.1e-5, 1.35], bConvert=False)
+            rotp.import_frame_vectors(fn)
+            for name, cls in (("R1", sd.spinRelaxationR1), ("R2", sd.spinRelaxationR2), ("NOE", sd.spinRelaxationNOE)):
+                ex = cls(name, "ps", w2, rotp, models)
+                for i in range(nR):
+                    ex.eval(ind=i)
+                res["csa_%s_600" % name] = np.stack((ex.values, ex.errors))
+            om = w.omega.copy(); fdd = w.get_factor_DD(); fcsa = w.get_factor_CSA()
+    x = rng.uniform(1e-6, 1e-2, 64); y = rng.uniform(0, 1e-2, 64)
+    save("relax.npz", hist=hist.astype(np.int64), edges_phi=edges[0], edges_cos=edges[1], params=np.array(pars),
+         zeta=zeta, Diso=2.1e-5, omega_600=om, f_dd=fdd, f_csa_600=fcsa, csa_array=csa,
+         jomega_x=x, jomega_y=y, jomega_out=npufunc.Jomega(x, y), jomega_outer=npufunc.Jomega.outer(x[:3], y[:5]),
+         jomega_f32=npufunc.Jomega(x.astype(np.float32), y.astype(np.float32)), **res)
+
+
+def main():
+    if not ref_loader.available():
+        sys.exit("reference tree not found at %s" % ref_loader.REFERENCE)
+    refct = ref_loader.script("calculate-Ct-from-traj.py")
+    refdq = ref_loader.script("calculate-dq-distribution.py")
+    golden_ct(refct)
+    golden_hist(refct)
+    golden_dq(refdq)
+    golden_fit()
+    golden_relax()
+
+
+if __name__ == "__main__":
+    main()

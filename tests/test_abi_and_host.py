@@ -1,0 +1,71 @@
+"""CPU-only checks: the C-ABI library builds, loads and exports every symbol the header declares;
+host-side mirrors of the reference helpers; the product refuses to run without CUDA."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from oracle import ct_oracle
+
+
+def _declared_symbols():
+    with open(os.path.join(ROOT, "include", "spinrelax_b200.h")) as fp:
+        text = fp.read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(sr_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from spinrelax_b200 import _lib, build
+    path = build.build()
+    assert os.path.exists(path)
+    lib = ctypes.CDLL(path)
+    names = _declared_symbols()
+    assert len(names) >= 10
+    for n in names:
+        assert hasattr(lib, n), "missing export %s" % n
+    assert _lib.load().sr_abi_version() == 1
+    # every declared symbol has a ctypes prototype in the binding
+    for n in names:
+        assert getattr(_lib.load(), n).argtypes is not None or n in ("sr_abi_version", "sr_last_error"), n
+
+
+def test_pure_abi_queries_work_without_gpu():
+    from spinrelax_b200 import _lib
+    lib = _lib.load()
+    pitch = lib.sr_ct_row_pitch(1000)
+    assert pitch >= 1000 + 480 and pitch % 8 == 0
+    assert lib.sr_ct_workspace_bytes(10, 1000, 76) >= 76 * 10 * pitch * 16 + 76 * 10 * 500 * 8
+
+
+def test_host_helpers_match_oracle(golden):
+    from spinrelax_b200 import ct
+    g = golden("ct_small.npz")
+    v4 = ct.reformat_vecs_by_tau([g["traj0"], g["traj1"]], 10.0, 2000.0)
+    assert np.array_equal(v4, g["vecs"])
+    assert np.array_equal(v4, ct_oracle.reformat_by_tau([g["traj0"], g["traj1"]], 10.0, 2000.0))
+    assert np.array_equal(ct.calculate_dt(10.0, 2000.0), g["dt"])
+    with pytest.raises(SystemExit):
+        ct.calculate_Ct_Palmer(np.zeros((4, 3)))          # reference exits on non-4D input (:213-216)
+
+
+def test_no_cpu_fallback():
+    import torch
+    from spinrelax_b200 import _lib, ct
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    with pytest.raises(_lib.SpinRelaxError):
+        ct.calculate_Ct_Palmer(np.zeros((2, 60, 3, 3), dtype=np.float32))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "spinrelax_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                with open(os.path.join(dirpath, f)) as fp:
+                    src = fp.read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f

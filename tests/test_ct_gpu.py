@@ -1,0 +1,127 @@
+"""GPU parity of the C(t) path (K2 pack, K1 lag sums, Palmer finalize) through the C ABI.
+
+Tolerances (north star): C(t) within 1e-6 relative of the reference evaluated on float64-upcast inputs;
+dC(t) gets the same bound on small cases and an absolute floor tied to C(t)'s 1e-6 where the spread
+across chunks is tiny."""
+import numpy as np
+import pytest
+
+from conftest import rel_err
+from oracle import ct_oracle
+
+pytestmark = pytest.mark.gpu
+
+RTOL_CT = 1e-6
+
+
+def _gpu_ct(v4):
+    from spinrelax_b200 import ct
+    return ct.calculate_Ct_Palmer(v4)
+
+
+def test_ct_small_vs_golden_and_oracle(golden):
+    g = golden("ct_small.npz")
+    Ct, dCt = _gpu_ct(g["vecs"])
+    assert Ct.dtype == np.float32 and Ct.shape == g["Ct64"].shape
+    assert rel_err(Ct, g["Ct64"]) < RTOL_CT
+    assert rel_err(dCt, g["dCt64"]) < 1e-5
+    oCt, odCt = ct_oracle.ct_palmer(g["vecs"].astype(np.float64))
+    assert rel_err(Ct, oCt) < RTOL_CT
+    # the float32 reference itself is further from float64 than we are
+    assert rel_err(Ct, g["Ct64"]) <= rel_err(g["Ct32"], g["Ct64"]) + 1e-7
+
+
+def test_ct_config1_vs_golden(golden):
+    from spinrelax_b200 import synth
+    g = golden("ct_config1.npz")
+    v = synth.nh_vectors(10000, 76, seed=int(g["seed"]))
+    v4 = v.reshape(10, 1000, 76, 3)
+    Ct, dCt = _gpu_ct(v4)
+    assert Ct.shape == (500, 76)
+    S = ct_oracle.ct_lag_sums_fft(v4)
+    oCt, odCt = ct_oracle.ct_from_lag_sums(S, 1000, dtype=np.float64)
+    assert rel_err(Ct, oCt) < RTOL_CT
+    assert np.max(np.abs(dCt - odCt)) < 1e-6 * np.max(np.abs(oCt))
+    if np.array_equal(v[:4], g["input_head"]):
+        lags = g["lags"]
+        assert rel_err(Ct[lags - 1], g["Ct64"]) < RTOL_CT
+
+
+def test_ct_lag_sums_raw(golden):
+    import torch
+    from spinrelax_b200 import ct
+    g = golden("ct_small.npz")
+    v = g["vecs"]
+    S = ct.ct_lag_sums_device(torch.from_numpy(v).cuda()).cpu().numpy()
+    assert rel_err(S, ct_oracle.ct_lag_sums_fft(v)) < 2e-7
+
+
+@pytest.mark.parametrize("shape", [(1, 2, 1), (1, 3, 2), (2, 51, 1), (3, 480, 4), (2, 961, 3), (2, 1921, 2),
+                                   (1, 2883, 1), (7, 100, 33), (2, 64, 130)])
+def test_ct_ragged_shapes(shape):
+    """Tile-boundary shapes: nF around the 960-frame tile and 480-lag tile, odd nF, tiny inputs."""
+    from spinrelax_b200 import synth
+    nC, nF, nR = shape
+    v4 = synth.nh_vectors(nC * nF, nR, seed=100 + nF).reshape(nC, nF, nR, 3)
+    with np.errstate(all="ignore"):
+        Ct, dCt = _gpu_ct(v4)
+        oCt, odCt = ct_oracle.ct_palmer(v4.astype(np.float64))
+    assert Ct.shape == (nF // 2, nR)
+    assert rel_err(Ct, oCt) < RTOL_CT
+    if nC > 1:
+        assert np.max(np.abs(dCt - odCt)) < 2e-6 * max(1e-3, float(np.max(np.abs(odCt))))
+    else:
+        assert np.all(np.isnan(dCt))          # G3: 0/0
+
+
+def test_ct_known_answers(golden):
+    g = golden("ct_edge.npz")
+    Ct, dCt = _gpu_ct(g["static"])
+    assert np.allclose(Ct, 1.0, atol=2e-7) and np.allclose(dCt, 0.0, atol=2e-7)
+    # i.i.d. uniform vectors: C(t) -> 0 within a few sigma = 1/sqrt(5 n)
+    rng = np.random.default_rng(3)
+    v = rng.standard_normal((4, 4000, 3, 3))
+    v = (v / np.linalg.norm(v, axis=-1, keepdims=True)).astype(np.float32)
+    Ct, _ = _gpu_ct(v)
+    assert np.max(np.abs(Ct)) < 6.0 / np.sqrt(5 * 4 * 2000)
+    # rotation invariance of C(t): pack with a PAF quaternion gives the same lag sums
+    import torch
+    from spinrelax_b200 import _lib
+    import ctypes
+    lib = _lib.load()
+    nC, nF, nR = 2, 700, 3
+    vt = torch.from_numpy(v[:nC, :nF].copy()).cuda()
+    pitch = lib.sr_ct_row_pitch(nF)
+    outs = []
+    for q in (None, (ctypes.c_double * 4)(0.83, -0.31, 0.22, 0.41)):
+        packed = torch.empty((nR, nC, pitch, 4), dtype=torch.float32, device="cuda")
+        S = torch.empty((nR, nC, nF // 2), dtype=torch.float64, device="cuda")
+        _lib.check(lib.sr_pack_vectors_f32(vt.data_ptr(), nC, nF, nR, q, packed.data_ptr(), pitch, None))
+        _lib.check(lib.sr_ct_lag_sums(packed.data_ptr(), pitch, nC, nF, nR, nF // 2, S.data_ptr(), None))
+        outs.append(S.cpu().numpy())
+    assert rel_err(outs[1], outs[0]) < 5e-6
+
+
+def test_ct_full_size_properties():
+    """BASELINE config-2 sized rows (nF = 2e5, L = 1e5) on 2 vectors: FFT oracle on every lag."""
+    import torch
+    from spinrelax_b200 import ct, synth
+    nC, nF, nR = 2, 200000, 2
+    v4 = synth.nh_vectors(nC * nF, nR, seed=77).reshape(nC, nF, nR, 3)
+    S = ct.ct_lag_sums_device(torch.from_numpy(v4).cuda()).cpu().numpy()
+    So = ct_oracle.ct_lag_sums_fft(v4)
+    assert S.shape == (nR, nC, 100000)
+    assert rel_err(S, So) < 1e-7
+    Ct, dCt = ct.ct_palmer_device(torch.from_numpy(v4).cuda())
+    oCt, _ = ct_oracle.ct_from_lag_sums(So, nF, dtype=np.float64)
+    assert rel_err(Ct.cpu().numpy(), oCt) < RTOL_CT
+
+
+def test_error_codes():
+    from spinrelax_b200 import _lib
+    lib = _lib.load()
+    assert lib.sr_ct_lag_sums(None, 100, 1, 10, 1, 5, None, None) == -1
+    assert b"null" in lib.sr_last_error()
+    import torch
+    x = torch.zeros(16, device="cuda")
+    assert lib.sr_ct_palmer_device(x.data_ptr(), 1, 100, 1, x.data_ptr(), x.data_ptr(), x.data_ptr(), 8, None) == -3
