@@ -73,6 +73,94 @@ int sr_ct_palmer_device(const float* d_vecs, int nC, long long nF, int nR, float
 /* Same through host buffers: H2D of vecs, compute, D2H of Ct/dCt (allocates its own scratch). */
 int sr_ct_palmer_host(const float* h_vecs, int nC, long long nF, int nR, float* h_Ct, float* h_dCt);
 
+/* ------------------------------------------------------------------------------------------------
+ * K3: PAF rotation + Lambert-cylindrical histogram, replaces calculate-Ct-from-traj.py:567 (rotation,
+ * transforms3d_supplement.py:270-296), :588 (gm.xyz_to_rtp, general_maths.py:143-158), :600-626
+ * (np.histogramdd per vector, bins (nbx, nby), range ((-pi,pi),(-1,1))).
+ *
+ * d_vecs: (nFrames, nR, 3) float32 AoS (the reference layout after the reshape at :535-536).
+ * h_q_rot: host pointer to (w,x,y,z) or NULL for no rotation (float32 path of the reference).
+ * d_edge_table: 2*(nbx+1) doubles (cos e_i, sin e_i of the phi edges) followed by the nby+1 cos(theta)
+ * edges, as np.histogramdd builds them.  Counts are ADDED into d_counts [nR][nbx][nby] (uint32).
+ * Samples closer than tol_phi (rad) / tol_cos to a bin edge are not counted; their flat sample index
+ * (frame*nR + r) is appended to d_amb_idx (up to amb_capacity; *d_amb_count keeps counting beyond it) so
+ * the caller can bin them with the reference's exact NumPy formula -- this is what makes the counts
+ * bit-identical to the reference without sharing its libm.
+ * ---------------------------------------------------------------------------------------------- */
+int sr_sphere_hist_table_doubles(int nbx, int nby);
+int sr_sphere_hist(const float* d_vecs, long long nFrames, int nR, const double* h_q_rot, int nbx, int nby,
+                   const double* d_edge_table, double tol_phi, double tol_cos, unsigned int* d_counts,
+                   long long* d_amb_idx, int amb_capacity, int* d_amb_count, void* stream);
+
+/* qs.rotate_vector_simd(v, q) (transforms3d_supplement.py:270-296) for n float32 vectors and one float64
+ * quaternion h_q (w,x,y,z; the caller normalises it as vecnorm_NDarray does): float64 output, bit-identical
+ * to NumPy (separately rounded products/sums in NumPy's order). */
+int sr_rotate_vectors_f32_f64(const float* d_v, long long n, const double* h_q, double* d_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K4: quaternion-displacement statistics over lag windows.
+ * Replaces the per-lag body of calculate-dq-distribution.py:554-625: obtain_self_dq (:102-109),
+ * average_anisotropic_tensor[_chunk] (:118-144) and average_LegendreP1quat[_chunk] (:111-135).
+ *
+ * d_q: (N, 4) float32 (w,x,y,z) orientation quaternions (float32 as read by plumedcolvario.py:68).
+ * d_lags: nLags frame lags (device, int64), each in [min_lag, N).  nCh >= 1 consecutive sub-chunks of
+ * ceil((N-lag)/nCh) samples (:129).  Output d_M [nLags][nCh][6] = sum_t of (xx, xy, xz, yy, yz, zz) of the
+ * vector part of conj(q_t) q_{t+lag}, float64.  Full-trajectory sums are the sum over chunks; means, the
+ * shipped iso moment 1-(2/3)sum|v|^2 (quirk G1), the intended 1-2<|v|^2> and R M R^T all derive on the host.
+ * ---------------------------------------------------------------------------------------------- */
+int sr_dq_moments(const float* d_q, long long N, const long long* d_lags, int nLags, long long min_lag, int nCh,
+                  double* d_M, void* stream);
+
+/* obtain_self_dq(q, delta): d_out (N-delta, 4) float64, imaged so that w >= 0 (quat_reduce_simd). */
+int sr_dq_self(const float* d_q, long long N, long long delta, double* d_out, void* stream);
+
+/* second moments of a float64 (n,3) vector list in nCh consecutive blocks: d_M [nCh][6]. */
+int sr_vec_second_moments(const double* d_v, long long n, int nCh, double* d_M, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K7: the npufunc.Jomega ufunc, Jomega/Jomega.c:49-66 (double loop) and :68-85 (float loop):
+ * out[i] = x[i] / (x[i]*x[i] + y[i]*y[i]) on n contiguous elements (the Python binding does the NumPy
+ * broadcasting / .outer); products, sum and quotient are rounded separately like the C loop.
+ * The reference's native loop signature is void(char **args, npy_intp *dimensions, npy_intp *steps, void*).
+ * ---------------------------------------------------------------------------------------------- */
+int sr_jomega_f64(const double* d_x, const double* d_y, double* d_out, long long n, void* stream);
+int sr_jomega_f32(const float* d_x, const float* d_y, float* d_out, long long n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K6: J(omega) -> R1 / R2 / NOE with weighted averaging over the bond-vector distribution.
+ * Replaces spectral_densities.py: update_A_coefficients :503-523 (caller builds A), calc_Jomega_one :552-557,
+ * _do_Jsum :1961-1972, isotropic calc_Jomega_one :430-443, spinRelaxationR1/R2/NOE.func :824-829, :859-864,
+ * :888-892 and check_and_calculate_average :751-763.
+ *
+ * sr_relax_a_moments: d_A (B,3) [or (nR,B,3) if per_residue_A] A_J coefficients of the bin vectors,
+ *   d_W (nR,B) weights (histogram counts).  d_amom (nR,10) = sum w, mean A (3), weighted covariance of A
+ *   (xx,xy,xz,yy,yz,zz).
+ * sr_relax_eval: one evaluation per (residue, field, CSA point).  h_D_J: host (3) D_J coefficients
+ *   (axisymmetric) or (1) D_iso when iso != 0.  Models: d_S2 (nR), d_C/d_tau (nR,max_comp), d_nComp (nR).
+ *   d_omega (nField,5) rad per time unit; d_f_csa (nField,nCSA), or (nField,nR) when csa_per_residue != 0
+ *   (then nCSA must be 1).  d_out (nR,nField,nCSA,6) = R1, R2, NOE, sigma_R1, sigma_R2, sigma_NOE; NOE uses
+ *   the bin-averaged R1 (:885-886); sigmas are 0 for isotropic tumbling.
+ * ---------------------------------------------------------------------------------------------- */
+int sr_relax_a_moments(const double* d_A, int per_residue_A, const double* d_W, int nR, int B, double* d_amom,
+                       void* stream);
+int sr_relax_eval(int iso, const double* h_D_J, double zeta, double time_fact, double gammaA, double gammaB,
+                  double f_dd, int nR, int nField, int nCSA, int csa_per_residue, int max_comp,
+                  const double* d_amom, const double* d_S2, const double* d_C, const double* d_tau,
+                  const int* d_nComp, const double* d_omega, const double* d_f_csa, double* d_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K5: batched bounded least-squares fit of C(t) = S2 + sum_i C_i exp(-t/tau_i), one CTA per residue.
+ * Replaces the scipy curve_fit call in autoCorrelationModel.conduct_curve_fitting,
+ * fitting_Ct_functions.py:322-324 (model :419-427, bounds :412-416, initial guess :359-374 built by caller).
+ * d_t, d_y, d_sigma: (nR, L) float64 (d_sigma may be NULL = unweighted).  Parameters ordered as the
+ * reference: C_1..C_nc, tau_1..tau_nc [, S2]; d_p0, d_lo, d_hi, d_popt are (nR, nParams).
+ * d_JtJ (nR, nParams, nParams) = J^T J of the sigma-weighted residuals at the optimum, d_cost (nR) =
+ * 0.5 sum r^2, d_status (nR, 2) = {1 ftol | 2 step below precision | 3 damping overflow | 0 max_iter, iterations}.
+ * ---------------------------------------------------------------------------------------------- */
+int sr_ct_fit_lm(const double* d_t, const double* d_y, const double* d_sigma, int nR, long long L, int nParams,
+                 const double* d_p0, const double* d_lo, const double* d_hi, int max_iter, double ftol,
+                 double* d_popt, double* d_JtJ, double* d_cost, int* d_status, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

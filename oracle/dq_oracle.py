@@ -181,7 +181,7 @@ def dq_curves(q, lags, ddt, nchunk=0, do_aniso=True):
 # ---- fits (host side in the product too; restated for the D-tensor parity tests) -------------------
 def _expdecay_cost(pos, x, y, C0, C1):
     """powell_expdecay, :152-167 (mean squared residual of C0 exp(-x/A) + C1)."""
-    A = pos
+    A = float(np.ravel(pos)[0])
     chi2 = 0.0
     for i in range(len(x)):
         chi2 += (C0 * math.exp(-x[i] / A) + C1 - y[i]) ** 2

@@ -30,6 +30,18 @@ def _declare(lib):
         "sr_ct_palmer_finalize": (i, [vp, i, ll, i, ll, vp, vp, vp]),
         "sr_ct_palmer_device": (i, [vp, i, ll, i, vp, vp, vp, sz, vp]),
         "sr_ct_palmer_host": (i, [vp, i, ll, i, vp, vp]),
+        "sr_sphere_hist_table_doubles": (i, [i, i]),
+        "sr_rotate_vectors_f32_f64": (i, [vp, ll, dp, vp, vp]),
+        "sr_jomega_f64": (i, [vp, vp, vp, ll, vp]),
+        "sr_jomega_f32": (i, [vp, vp, vp, ll, vp]),
+        "sr_relax_a_moments": (i, [vp, i, vp, i, i, vp, vp]),
+        "sr_relax_eval": (i, [i, dp, _c.c_double, _c.c_double, _c.c_double, _c.c_double, _c.c_double, i, i, i, i, i,
+                              vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+        "sr_ct_fit_lm": (i, [vp, vp, vp, i, ll, i, vp, vp, vp, i, _c.c_double, vp, vp, vp, vp, vp]),
+        "sr_dq_moments": (i, [vp, ll, vp, i, ll, i, vp, vp]),
+        "sr_dq_self": (i, [vp, ll, ll, vp, vp]),
+        "sr_vec_second_moments": (i, [vp, ll, i, vp, vp]),
+        "sr_sphere_hist": (i, [vp, ll, i, dp, i, i, vp, _c.c_double, _c.c_double, vp, vp, i, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

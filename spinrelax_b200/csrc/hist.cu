@@ -12,7 +12,6 @@
 namespace {
 
 constexpr int kHistThreads = 256;
-constexpr int kMaxGroup = 8;   // vectors per CTA (shared-memory privatised histograms)
 
 struct HistParams {
   double R[9];        // rotation matrix (row major), identity when no rotation
@@ -67,43 +66,68 @@ __device__ __forceinline__ int classify(double x, double y, double z, const Hist
   return 0;
 }
 
-// grid.x = frame blocks, grid.y = vector groups of `group` vectors
+// grid.x = vector groups (fastest, so CTAs sharing a frame range run together and the 64-byte DRAM
+// blocks that straddle two groups are fetched once), grid.y = frame blocks.  `group` = 1 << gshift vectors
+// per CTA; bins are privatised in shared memory as packed 16-bit counters (a CTA sees < 65536 frames).
 __global__ void __launch_bounds__(kHistThreads)
-sphere_hist_kernel(const float* __restrict__ vecs, long long nFrames, int nR, int group, long long framesPerBlock,
+sphere_hist_kernel(const float* __restrict__ vecs, long long nFrames, int nR, int gshift, int framesPerBlock,
                    HistParams p, const double2* __restrict__ edge_dir, const double* __restrict__ edge_cos,
                    unsigned int* __restrict__ counts, long long* __restrict__ amb_idx, int amb_capacity,
                    int* __restrict__ amb_count) {
   extern __shared__ unsigned int sh_hist[];
   const int nbins = p.nbx * p.nby;
-  const int r0 = blockIdx.y * group;
+  const int group = 1 << gshift;
+  const int r0 = blockIdx.x * group;
   const int nv = min(group, nR - r0);
-  for (int i = threadIdx.x; i < nv * nbins; i += kHistThreads) sh_hist[i] = 0u;
+  const int nwords = (nv * nbins + 1) >> 1;
+  for (int i = threadIdx.x; i < nwords; i += kHistThreads) sh_hist[i] = 0u;
   __syncthreads();
 
-  const long long f0 = (long long)blockIdx.x * framesPerBlock;
-  const long long f1 = min(nFrames, f0 + framesPerBlock);
-  const long long nSamp = (f1 - f0) * nv;
-  for (long long s = threadIdx.x; s < nSamp; s += kHistThreads) {
-    const int vl = (int)(s % nv);
-    const long long f = f0 + s / nv;
-    const float* src = vecs + (f * nR + r0 + vl) * 3;
-    const double vx = (double)__ldg(src), vy = (double)__ldg(src + 1), vz = (double)__ldg(src + 2);
-    const double x = p.R[0] * vx + p.R[1] * vy + p.R[2] * vz;
-    const double y = p.R[3] * vx + p.R[4] * vy + p.R[5] * vz;
-    const double z = p.R[6] * vx + p.R[7] * vy + p.R[8] * vz;
-    int bin = 0;
-    const int cls = classify(x, y, z, p, edge_dir, edge_cos, bin);
-    if (cls == 0) {
-      atomicAdd(&sh_hist[vl * nbins + bin], 1u);
-    } else if (cls == 2) {
-      const int slot = atomicAdd(amb_count, 1);
-      if (slot < amb_capacity) amb_idx[slot] = f * nR + r0 + vl;
+  const long long f0 = (long long)blockIdx.y * framesPerBlock;
+  const int nfl = (int)min((long long)framesPerBlock, nFrames - f0);
+  const int nSamp = nfl << gshift;
+  const float* base = vecs + (f0 * nR + r0) * 3;
+  const int rowStride = nR * 3;
+  constexpr int U = 4;
+  for (int s0 = threadIdx.x; s0 < nSamp; s0 += kHistThreads * U) {
+    float vx[U], vy[U], vz[U];
+    bool on[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int s = s0 + u * kHistThreads;
+      const int vl = s & (group - 1), fl = s >> gshift;
+      on[u] = (s < nSamp) && (vl < nv);
+      vx[u] = vy[u] = vz[u] = 0.f;
+      if (on[u]) {
+        const float* src = base + (long long)fl * rowStride + vl * 3;
+        vx[u] = __ldg(src); vy[u] = __ldg(src + 1); vz[u] = __ldg(src + 2);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (!on[u]) continue;
+      const int s = s0 + u * kHistThreads;
+      const int vl = s & (group - 1), fl = s >> gshift;
+      const double dx = vx[u], dy = vy[u], dz = vz[u];
+      const double x = p.R[0] * dx + p.R[1] * dy + p.R[2] * dz;
+      const double y = p.R[3] * dx + p.R[4] * dy + p.R[5] * dz;
+      const double z = p.R[6] * dx + p.R[7] * dy + p.R[8] * dz;
+      int bin = 0;
+      const int cls = classify(x, y, z, p, edge_dir, edge_cos, bin);
+      if (cls == 0) {
+        const int k = vl * nbins + bin;
+        atomicAdd(&sh_hist[k >> 1], 1u << ((k & 1) << 4));
+      } else if (cls == 2) {
+        const int slot = atomicAdd(amb_count, 1);
+        if (slot < amb_capacity) amb_idx[slot] = (f0 + fl) * nR + r0 + vl;
+      }
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < nv * nbins; i += kHistThreads) {
-    const unsigned int c = sh_hist[i];
-    if (c) atomicAdd(&counts[(long long)r0 * nbins + i], c);
+  for (int i = threadIdx.x; i < nwords; i += kHistThreads) {
+    const unsigned int w = sh_hist[i];
+    if (w & 0xffffu) atomicAdd(&counts[(long long)r0 * nbins + 2 * i], w & 0xffffu);
+    if (w >> 16) atomicAdd(&counts[(long long)r0 * nbins + 2 * i + 1], w >> 16);
   }
 }
 
@@ -137,28 +161,61 @@ extern "C" int sr_sphere_hist(const float* d_vecs, long long nFrames, int nR, co
   SR_CUDA(cudaGetDevice(&dev));
   SR_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   SR_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  // two CTAs per SM: at most ~100 KB of privatised bins each
-  int group = (int)((size_t)100 * 1024 / ((size_t)nbins * 4));
-  if (group > kMaxGroup) group = kMaxGroup;
-  if (group > nR) group = nR;
-  if (group < 1) {
-    group = 1;
-    SR_REQUIRE((size_t)nbins * 4 <= (size_t)max_smem, "sr_sphere_hist: %d bins do not fit in shared memory", nbins);
-  }
-  const size_t smem = (size_t)group * nbins * 4;
+  // two CTAs per SM: at most ~100 KB of privatised 16-bit bins each; group is a power of two <= 16
+  int gshift = 4;
+  while (gshift > 0 && (((size_t)(1 << gshift) * nbins + 1) / 2) * 4 > (size_t)100 * 1024) --gshift;
+  while (gshift > 0 && (1 << (gshift - 1)) >= nR) --gshift;
+  const int group = 1 << gshift;
+  const size_t smem = (((size_t)group * nbins + 1) / 2) * 4;
+  SR_REQUIRE(smem <= (size_t)max_smem, "sr_sphere_hist: %d bins do not fit in shared memory", nbins);
   SR_CUDA(cudaFuncSetAttribute(sphere_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int nGroups = (nR + group - 1) / group;
-  long long nFB = (4LL * 2 * sms + nGroups - 1) / nGroups;     // ~4 waves of 2 CTAs/SM
+  long long nFB = (6LL * 2 * sms + nGroups - 1) / nGroups;     // ~6 waves of 2 CTAs/SM
   long long fpb = (nFrames + nFB - 1) / nFB;
-  if (fpb < 256) fpb = 256;
+  if (fpb < 64) fpb = 64;
+  if (fpb > 32768) fpb = 32768;                                 // 16-bit counters: fewer than 65536 frames per CTA
   nFB = (nFrames + fpb - 1) / fpb;
-  SR_REQUIRE(nGroups <= 65535, "sr_sphere_hist: too many vector groups");
-  dim3 grid((unsigned)nFB, (unsigned)nGroups);
+  SR_REQUIRE(nFB <= 65535, "sr_sphere_hist: %lld frame blocks exceed the grid limit", nFB);
+  dim3 grid((unsigned)nGroups, (unsigned)nFB);
   const double2* edge_dir = (const double2*)d_edge_table;
   const double* edge_cos = d_edge_table + 2 * (nbx + 1);
-  sphere_hist_kernel<<<grid, kHistThreads, smem, (cudaStream_t)stream>>>(d_vecs, nFrames, nR, group, fpb, p, edge_dir,
+  sphere_hist_kernel<<<grid, kHistThreads, smem, (cudaStream_t)stream>>>(d_vecs, nFrames, nR, gshift, (int)fpb, p, edge_dir,
                                                                          edge_cos, d_counts, d_amb_idx, amb_capacity,
                                                                          d_amb_count);
+  SR_CUDA(cudaGetLastError());
+  return SR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// rotate_vector_simd (transforms3d_supplement.py:270-296) for float32 vectors and one float64 quaternion:
+// float64 result, every product and sum rounded separately in NumPy's order so the output is bit-identical.
+// ------------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256)
+rotate_f32_f64_kernel(const float* __restrict__ v, long long n, double qw, double qx, double qy, double qz,
+                      double* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double vx = v[3 * i], vy = v[3 * i + 1], vz = v[3 * i + 2];
+  // a = cross(q_v, v) + q_w * v
+  const double ax = __dadd_rn(__dsub_rn(__dmul_rn(qy, vz), __dmul_rn(qz, vy)), __dmul_rn(qw, vx));
+  const double ay = __dadd_rn(__dsub_rn(__dmul_rn(qz, vx), __dmul_rn(qx, vz)), __dmul_rn(qw, vy));
+  const double az = __dadd_rn(__dsub_rn(__dmul_rn(qx, vy), __dmul_rn(qy, vx)), __dmul_rn(qw, vz));
+  // b = cross(q_v, a) ; out = b + b + v
+  const double bx = __dsub_rn(__dmul_rn(qy, az), __dmul_rn(qz, ay));
+  const double by = __dsub_rn(__dmul_rn(qz, ax), __dmul_rn(qx, az));
+  const double bz = __dsub_rn(__dmul_rn(qx, ay), __dmul_rn(qy, ax));
+  out[3 * i] = __dadd_rn(__dadd_rn(bx, bx), vx);
+  out[3 * i + 1] = __dadd_rn(__dadd_rn(by, by), vy);
+  out[3 * i + 2] = __dadd_rn(__dadd_rn(bz, bz), vz);
+}
+}  // namespace
+
+extern "C" int sr_rotate_vectors_f32_f64(const float* d_v, long long n, const double* h_q, double* d_out, void* stream) {
+  SR_REQUIRE(d_v && h_q && d_out, "sr_rotate_vectors_f32_f64: null pointer");
+  SR_REQUIRE(n >= 1, "sr_rotate_vectors_f32_f64: empty input");
+  rotate_f32_f64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_v, n, h_q[0], h_q[1], h_q[2],
+                                                                                     h_q[3], d_out);
   SR_CUDA(cudaGetLastError());
   return SR_OK;
 }

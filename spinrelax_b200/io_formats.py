@@ -1,0 +1,113 @@
+"""Boundary text formats either side of the hot path (readers/writers only, no numerics):
+
+  read_from_plumedprint   plumedcolvario.py:24-81   (PLUMED PRINT file -> float32 (nfields, ndata))
+  print_xylist            general_scripts.py:246-273 (-aniso_q.dat, -tensor.dat, _S2.dat, _avgvec.dat)
+  print_sxylist           general_scripts.py:275-290 (_Ctint.dat / _Ctext.dat, xmgrace sets with legends)
+  load_sxydylist          general_scripts.py:182-213 (reads them back for the fitting stage)
+"""
+import numpy as np
+
+
+def read_from_plumedprint(fname):
+    """Returns [field_names, data] with data float32 of shape (nfields, ndata); every value is rounded
+    to float32 exactly like the reference's per-token np.float32() (quirk G2: including the time column)."""
+    names = None
+    rows = []
+    with open(fname) as fp:
+        for line in fp:
+            if line == '\n':
+                continue
+            if line.startswith("#"):
+                tok = line.split()
+                if len(tok) > 1 and tok[1] == "FIELDS":
+                    found = tok[2:]
+                    if names is None:
+                        names = found
+                    elif any(a != b for a, b in zip(names, found)):
+                        print('= = ERROR: Multiple FIELD headers are present to indicate parallel trajectoreies, '
+                              'but their entries do not agree!')
+                        print(names)
+                        print(found)
+                        return -1
+                continue
+            if names is None:
+                print('= = ERROR: Data-like line encountered before a FIELDS definition! Line as follows:')
+                print(line)
+                return -1
+            tok = line.split()
+            if len(tok) != len(names):
+                print('= = ERROR: Data-like line does not have the same number of fields as defined in FIELDS! ( %i )'
+                      % len(names))
+                print(tok)
+                return -1
+            rows.append(tok)
+    data = np.array(rows, dtype=np.float64).astype(np.float32).T.copy(order='F') if rows else \
+        np.zeros((len(names or []), 0), dtype=np.float32)
+    print('= = Input file %s has been read: Found %i data-like lines in input plumed FES file.' % (fname, data.shape[1]))
+    print('= = = %i field entries discovered. Field entries are as follows:' % len(names))
+    print(str(names).strip('[]'))
+    return names, data
+
+
+def print_xylist(fn, x, ylist, bCols=False, header=""):
+    """x (nvals), ylist (nplots, nvals); bCols puts all plots on one line (`%g` columns)."""
+    ylist = np.array(ylist)
+    with open(fn, 'w') as fp:
+        if header != "":
+            print(header, file=fp)
+        if ylist.ndim == 1:
+            for j in range(len(x)):
+                print(x[j], ylist[j], file=fp)
+            print("&", file=fp)
+        elif ylist.ndim == 2:
+            if bCols:
+                for j in range(ylist.shape[1]):
+                    print("%g " % x[j] + " ".join("%g" % ylist[i][j] for i in range(ylist.shape[0])), file=fp)
+                print("&", file=fp)
+            else:
+                for i in range(ylist.shape[0]):
+                    for j in range(len(x)):
+                        print(x[j], ylist[i][j], file=fp)
+                    print("&", file=fp)
+
+
+def print_sxylist(fn, legend, x, ylist, header=[]):
+    """One xmgrace set per legend entry; each row is `x` followed by str() of the y-row without brackets."""
+    ylist = np.array(ylist)
+    with open(fn, 'w') as fp:
+        for line in header:
+            print("%s" % line, file=fp)
+        for s in range(len(ylist)):
+            print("@s%d legend \"%s\"" % (s, legend[s]), file=fp)
+            for j in range(len(x)):
+                print(x[j], str(ylist[s][j]).strip('[]'), file=fp)
+            print("&", file=fp)
+
+
+def load_sxydylist(fn, key="legend"):
+    """Reads xmgrace sets `x y [dy]` separated by `&`; returns legends, x, y, dy arrays (dy=[] when absent)."""
+    legs, xs, ys, dys = [], [], [], []
+    x, y, dy = [], [], []
+    with open(fn) as fp:
+        for l in fp:
+            if l == "" or l == "\n":
+                continue
+            tok = l.split()
+            if l[0] in "#@":
+                if key in l:
+                    legs.append(tok[-1].strip('"'))
+                continue
+            if l[0] == "&":
+                xs.append(x); ys.append(y)
+                if len(dy) > 0:
+                    dys.append(dy)
+                x, y, dy = [], [], []
+                continue
+            x.append(float(tok[0])); y.append(float(tok[1]))
+            if len(tok) > 2:
+                dy.append(float(tok[2]))
+    if x != []:
+        xs.append(x); ys.append(y); dys.append(dy)
+    if dys != []:
+        return legs, np.array(xs), np.array(ys), np.array(dys)
+    return legs, np.array(xs), np.array(ys), []

@@ -65,7 +65,7 @@ class CtHistStep:
             self._timed("sphere_hist_kernel",
                         lambda: self._hist.accumulate_device(v_dev.view(nC * nF, nR, 3), self.q_rot, reset=True),
                         time_kernels)
-            hist = self._hist.counts
+            hist = self._hist.finish(v_dev, self.q_rot)     # ambiguous-sample tie-break + D2H of the counts
         if self.world > 1:
             import torch.distributed as dist
             mine = self.torch.stack((self.Ct, self.dCt))
@@ -73,18 +73,16 @@ class CtHistStep:
         return self.Ct, self.dCt, hist
 
     def run_host(self, v_np):
-        """Public host-buffer path: NumPy in, NumPy out (H2D + kernels + D2H inside)."""
-        Ct, dCt = ct.calculate_Ct_Palmer_quiet(v_np)
-        hist = None
-        if self.has_hist:
-            from . import hist as _hist
-            hist, _ = _hist.sphere_histogram(v_np.reshape(self.nC * self.nF, self.nR, 3), self.q_rot, self.nbx)
-        if self.world > 1:
-            import torch.distributed as dist
-            mine = self.torch.from_numpy(np.stack((Ct, dCt))).to(self.dev)
-            dist.gather(mine, self.gathered if self.rank == 0 else None, dst=0)
-            self.torch.cuda.synchronize()
-        return Ct, dCt, hist
+        """Public host-buffer path: NumPy (nC, nF, nR, 3) float32 in, NumPy out.  One H2D of the vectors
+        (pinned memory is copied asynchronously), the same kernels as run_device, D2H of Ct, dCt, counts."""
+        torch = self.torch
+        v = np.ascontiguousarray(v_np, dtype=np.float32)
+        v_dev = torch.from_numpy(v).to(self.dev, non_blocking=True)
+        Ct, dCt, hist = self.run_device(v_dev)
+        out = torch.stack((Ct, dCt)).cpu().numpy()
+        if hist is not None:
+            hist = hist.astype(np.float64)
+        return out[0], out[1], hist
 
     # -------------------------------------------------------------------------------------------
     def reset_kernel_timers(self):

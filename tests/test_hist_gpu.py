@@ -1,0 +1,82 @@
+"""GPU parity of K3 (rotation + spherical histogram): counts must equal np.histogramdd's bit for bit."""
+import numpy as np
+import pytest
+
+from oracle import ct_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _gpu_hist(v, q, nbx=72):
+    from spinrelax_b200 import hist
+    return hist.sphere_histogram(v, q, nbx)
+
+
+def test_hist_golden_rotated(golden):
+    g = golden("hist.npz")
+    h, e = _gpu_hist(g["vecs_rot"], g["q"])
+    assert h.dtype == np.float64 and h.shape == (7, 72, 36)
+    assert np.array_equal(h.astype(np.int64), g["hist_rot"])
+    assert np.array_equal(e[0], g["edges_phi"]) and np.array_equal(e[1], g["edges_cos"])
+    h36, _ = _gpu_hist(g["vecs_rot36"], g["q"], 36)
+    assert np.array_equal(h36.astype(np.int64), g["hist_rot36"])
+
+
+def test_hist_golden_float32_path_and_special(golden):
+    g = golden("hist.npz")
+    h, _ = _gpu_hist(g["vecs_f32"], None)
+    assert h.dtype == np.float32
+    assert np.array_equal(h.astype(np.int64), g["hist_f32"])
+    hs, _ = _gpu_hist(g["special"], None)       # +-z, +-x, +y, zero vector: on-edge and NaN semantics
+    assert np.array_equal(hs.astype(np.int64), g["hist_special"])
+
+
+@pytest.mark.parametrize("nR,frames,rot", [(1, 1, True), (3, 257, True), (76, 5000, True), (76, 5000, False),
+                                            (9, 20000, True), (130, 999, True)])
+def test_hist_vs_oracle_same_host(nR, frames, rot):
+    """Unfiltered samples, oracle run on the same host (NumPy decides the ties on both sides)."""
+    from spinrelax_b200 import synth
+    v = synth.nh_vectors(frames, nR, seed=900 + nR)
+    q = np.array([0.2, 0.5, -0.7, 0.1]) if rot else None
+    h, _ = _gpu_hist(v, q)
+    ho, _ = ct_oracle.sphere_histogram(v, q)
+    assert np.array_equal(h.astype(np.int64), ho.astype(np.int64))
+    assert h.sum() == frames * nR
+
+
+def test_hist_uniform_sphere_and_ties():
+    """Uniform vectors touch every bin; axis-aligned and grid-aligned vectors sit exactly on edges."""
+    rng = np.random.default_rng(5)
+    v = rng.standard_normal((40000, 4, 3))
+    v = (v / np.linalg.norm(v, axis=-1, keepdims=True)).astype(np.float32)
+    # exact edge directions: phi = k*5deg in the xy plane, cos(theta) = j/18
+    k = np.arange(72)
+    edge = np.stack((np.cos(np.deg2rad(5.0 * k - 180)), np.sin(np.deg2rad(5.0 * k - 180)), np.zeros(72)), axis=1)
+    v[:72, 0] = edge.astype(np.float32)
+    j = np.linspace(-1, 1, 37)
+    v[100:137, 1] = np.stack((np.sqrt(1 - j * j), np.zeros(37), j), axis=1).astype(np.float32)
+    for q in (None, np.array([1.0, 0, 0, 0]), np.array([0.83, -0.31, 0.22, 0.41])):
+        with np.errstate(all="ignore"):
+            h, _ = _gpu_hist(v, q)
+            ho, _ = ct_oracle.sphere_histogram(v, q)
+        assert np.array_equal(h.astype(np.int64), ho.astype(np.int64))
+        assert (h > 0).all()
+
+
+def test_hist_full_size_sum():
+    """BASELINE config-2 sized stream (1e6 frames x 76): every unit vector is counted exactly once."""
+    import torch
+    from spinrelax_b200 import hist, synth
+    v = synth.nh_vectors(1000000, 76, seed=77)
+    acc = hist.SphereHistogram(76)
+    vd = torch.from_numpy(v).cuda()
+    q = np.array([0.83, -0.31, 0.22, 0.41])
+    acc.accumulate_device(vd, q)
+    counts = acc.finish(vd, q)
+    assert counts.sum() == 76 * 1000000 and (counts.sum(axis=(1, 2)) == 1000000).all()
+    assert acc.last_ambiguous < 100
+    # a 1/50 slice against the oracle
+    sl = v[::50]
+    h, _ = hist.sphere_histogram(sl, q)
+    ho, _ = ct_oracle.sphere_histogram(sl, q)
+    assert np.array_equal(h.astype(np.int64), ho.astype(np.int64))

@@ -98,6 +98,54 @@ __global__ void __launch_bounds__(256) k_ffma2(float* out, int iters, float x0, 
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+__device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm volatile("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// ---- 3b. the K1 pattern with packed FFMA2: window frames as aligned pairs, two accumulator pairings
+// (A: left vector of step t, B: left vector of step t+1), R lags per lane, no loads
+template <int R>
+__global__ void __launch_bounds__(256) k_p2pattern_ffma2(float* out, int iters, float seed) {
+  constexpr int H = R / 2;
+  uint64_t X2[H], Y2[H], Z2[H], accA[H], accB[H];
+#pragma unroll
+  for (int m = 0; m < H; ++m) {
+    X2[m] = pack2(seed + 0.01f * m + threadIdx.x * 1e-4f, seed - 0.01f * m);
+    Y2[m] = pack2(seed - 0.02f * m, seed + 0.02f * m);
+    Z2[m] = pack2(0.5f * seed + 0.003f * m, 0.4f * seed);
+    accA[m] = 0ull; accB[m] = 0ull;
+  }
+  float ax = seed * 0.3f, ay = seed * 0.4f, az = seed * 0.5f, bx = seed * 0.2f, by = seed * 0.1f, bz = seed * 0.6f;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int k = 0; k < H; ++k) {       // one step pair (t, t+1) per k; window slides by one aligned pair
+      const uint64_t AX = pack2(ax, ax), AY = pack2(ay, ay), AZ = pack2(az, az);
+      const uint64_t BX = pack2(bx, bx), BY = pack2(by, by), BZ = pack2(bz, bz);
+#pragma unroll
+      for (int m = 0; m < H; ++m) {
+        const int s = (k + m) % H;
+        uint64_t d = fmul2(AX, X2[s]);
+        d = ffma2(AY, Y2[s], d);
+        d = ffma2(AZ, Z2[s], d);
+        accA[m] = ffma2(d, d, accA[m]);
+        uint64_t e = fmul2(BX, X2[s]);
+        e = ffma2(BY, Y2[s], e);
+        e = ffma2(BZ, Z2[s], e);
+        accB[m] = ffma2(e, e, accB[m]);
+      }
+      X2[k] += 0x0000000100000001ull;   // fake slide
+      ax += 1e-8f; bx += 1e-8f;
+    }
+  }
+  float sum = 0.f;
+#pragma unroll
+  for (int m = 0; m < H; ++m)
+    sum += __uint_as_float((uint32_t)accA[m]) + __uint_as_float((uint32_t)(accA[m] >> 32)) +
+           __uint_as_float((uint32_t)accB[m]) + __uint_as_float((uint32_t)(accB[m] >> 32));
+  out[blockIdx.x * blockDim.x + threadIdx.x] = sum;
+}
+
 // ---- 4. DFMA chains ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_dfma(double* out, int iters, double x0, double y0) {
   double acc[8], x[4], y[2];
@@ -256,6 +304,15 @@ int main() {
     ms = time_ms([&] { k_p2pattern<16><<<grid, block>>>(d, iters, 0.7f); });
     pairs = nthr * iters * 16 * 16;
     printf("{\"probe\":\"p2pattern_R16\",\"ms\":%.3f,\"pairs_per_s\":%.4g,\"tflops7\":%.2f}\n", ms, pairs / ms * 1e3, pairs * 7 / ms * 1e-9);
+  }
+  {
+    int iters = 3000;
+    float ms = time_ms([&] { k_p2pattern_ffma2<12><<<grid, block>>>(d, iters, 0.7f); });
+    double pairs = nthr * iters * 6.0 * 6 * 4;      // H step-pairs x H window pairs x (2 lags x 2 left vectors)
+    printf("{\"probe\":\"p2pattern_ffma2_R12\",\"ms\":%.3f,\"pairs_per_s\":%.4g,\"tflops7\":%.2f}\n", ms, pairs / ms * 1e3, pairs * 7 / ms * 1e-9);
+    ms = time_ms([&] { k_p2pattern_ffma2<16><<<grid, block>>>(d, iters, 0.7f); });
+    pairs = nthr * iters * 8.0 * 8 * 4;
+    printf("{\"probe\":\"p2pattern_ffma2_R16\",\"ms\":%.3f,\"pairs_per_s\":%.4g,\"tflops7\":%.2f}\n", ms, pairs / ms * 1e3, pairs * 7 / ms * 1e-9);
   }
   {
     int iters = 20000;
