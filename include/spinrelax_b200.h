@@ -62,6 +62,10 @@ int sr_pack_vectors_f32(const float* d_vecs, int nC, long long nF, int nR, const
 int sr_ct_lag_sums(const void* d_packed, long long pitch, int nC, long long nF, int nR, long long L,
                    double* d_S, void* stream);
 
+/* Same kernel with an explicit tile configuration (tuning / profiling only; 0 .. 7, see csrc/ct.cu). */
+int sr_ct_lag_sums_variant(const void* d_packed, long long pitch, int nC, long long nF, int nR, long long L,
+                           double* d_S, int variant, void* stream);
+
 /* per-chunk mean -> mean and std/(sqrt(nC)-1) over chunks (:226-228). */
 int sr_ct_palmer_finalize(const double* d_S, int nC, long long nF, int nR, long long L, float* d_Ct,
                           float* d_dCt, void* stream);
@@ -91,6 +95,12 @@ int sr_sphere_hist_table_doubles(int nbx, int nby);
 int sr_sphere_hist(const float* d_vecs, long long nFrames, int nR, const double* h_q_rot, int nbx, int nby,
                    const double* d_edge_table, double tol_phi, double tol_cos, unsigned int* d_counts,
                    long long* d_amb_idx, int amb_capacity, int* d_amb_count, void* stream);
+
+/* Per (block of framesPerBlock frames, vector) sums of x,y,z,xx,xy,xz,yy,yz,zz (FP64) of (nFrames, nR, 3) float32
+ * vectors: the reductions behind --vecAvg (calculate-Ct-from-traj.py:579-583) and --S2
+ * (calculate_S2_by_outerProduct :96-145).  d_out [nBlocks][nR][9], nBlocks = ceil(nFrames/framesPerBlock). */
+int sr_vec_block_moments(const float* d_vecs, long long nFrames, int nR, long long framesPerBlock, double* d_out,
+                         void* stream);
 
 /* qs.rotate_vector_simd(v, q) (transforms3d_supplement.py:270-296) for n float32 vectors and one float64
  * quaternion h_q (w,x,y,z; the caller normalises it as vecnorm_NDarray does): float64 output, bit-identical

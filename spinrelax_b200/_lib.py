@@ -27,10 +27,12 @@ def _declare(lib):
         "sr_ct_workspace_bytes": (sz, [i, ll, i]),
         "sr_pack_vectors_f32": (i, [vp, i, ll, i, dp, vp, ll, vp]),
         "sr_ct_lag_sums": (i, [vp, ll, i, ll, i, ll, vp, vp]),
+        "sr_ct_lag_sums_variant": (i, [vp, ll, i, ll, i, ll, vp, i, vp]),
         "sr_ct_palmer_finalize": (i, [vp, i, ll, i, ll, vp, vp, vp]),
         "sr_ct_palmer_device": (i, [vp, i, ll, i, vp, vp, vp, sz, vp]),
         "sr_ct_palmer_host": (i, [vp, i, ll, i, vp, vp]),
         "sr_sphere_hist_table_doubles": (i, [i, i]),
+        "sr_vec_block_moments": (i, [vp, ll, i, ll, vp, vp]),
         "sr_rotate_vectors_f32_f64": (i, [vp, ll, dp, vp, vp]),
         "sr_jomega_f64": (i, [vp, vp, vp, ll, vp]),
         "sr_jomega_f32": (i, [vp, vp, vp, ll, vp]),

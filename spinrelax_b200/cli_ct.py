@@ -1,0 +1,172 @@
+"""CLI mirror of calculate-Ct-from-traj.py for the part of it that is on the hot path.
+
+    python -m spinrelax_b200.cli_ct -s ref.pdb -f vecs.npy [vecs2.npy ...] --dt 10 --tau 5000 -o rotdif \
+           --vecRot "qw qx qy qz" --vecHist --binary --vecAvg --S2 --Ct
+
+Flags and defaults are the reference's (:303-345).  What is NOT reproduced is the mdtraj front end
+(trajectory reading, centring, superposition, atom selections, :396-498 -- out of scope):
+`-f` takes the unit X-H vector trajectories themselves, one `.npy` (frames, bonds, 3) array -- or `.npz` with
+`vecs` [, `vecs_unfitted`, `names`, `dt`] -- per trajectory, i.e. exactly what obtain_XHvecs (:64-86) returns
+after the fit.  Everything downstream is the reference's flow: reformat by tau (:513-516), C(t) (:527-531),
+reshape (:535-536), PAF rotation (:567), average vector (:579-583), spherical histogram (:585-630), S2 (:638-646),
+written to the same files in the same formats.
+"""
+import argparse
+import sys
+import time
+
+import numpy as np
+
+from . import ct, hist, io_formats
+
+
+def build_parser():
+    p = argparse.ArgumentParser(description='Obtain the unit X-H vectors from one of more trajectories,'
+                                'and conduct calculations on it, such as S^2, C(t), and others analyses.',
+                                formatter_class=argparse.ArgumentDefaultsHelpFormatter)
+    p.add_argument('-s', type=str, dest='topfn', required=False, nargs='+', default=[],
+                   help='Topology file(s); accepted for command-line compatibility, not read on this path.')
+    p.add_argument('-f', '--infn', type=str, dest='infn', required=True, nargs='+',
+                   help='One or more X-H vector trajectories (.npy / .npz). Multiple trajectories are analysed '
+                        'separately in C(t)-calculations, but otherwise aggregated.')
+    p.add_argument('-o', '--outpref', type=str, dest='out_pref', default='out', help='Output file prefix.')
+    p.add_argument('--split', type=int, dest='nSplitFrames', default=-1, help='Accepted, unused.')
+    p.add_argument('--dt', type=float, dest='dt', default=None,
+                   help='Time between frames (the reference reads it from the trajectory); default: npz `dt` or 1.0.')
+    p.add_argument('-t', '--tau', type=float, dest='tau', default=None,
+                   help='An estimate of the global tumbling time that is used to ignore internal motions '
+                        'on timescales larger than can be measured by NMR relaxation.')
+    p.add_argument('--prefact', type=float, dest='zeta', default=(1.02 / 1.04) ** 6,
+                   help='MD-specific prefactor that accounts for librations of the XH-vector not seen in classical MD.')
+    p.add_argument('--S2', dest='bDoS2', action='store_true', default=False, help='Calculate order parameters S2.')
+    p.add_argument('--Ct', dest='bDoCt', action='store_true', default=False, help='Calculate autocorrelation Ct.')
+    p.add_argument('--vecDist', dest='bDoVecDistrib', action='store_true', default=False,
+                   help='Print the vectors distribution in spherical coordinates.')
+    p.add_argument('--binary', action='store_true', default=False, help='Store distributions as numpy binaries.')
+    p.add_argument('--vecHist', dest='bDoVecHist', action='store_true', default=False,
+                   help='Print the 2D-histogram rather than just the collection of vecs.')
+    p.add_argument('--histBin', type=int, default=72,
+                   help='Number of bins along phi (-pi,pi); the number of bins along cos(theta) is half of it.')
+    p.add_argument('--vecAvg', dest='bDoVecAverage', action='store_true', default=False,
+                   help='Print the average unit XH-vector.')
+    p.add_argument('--vecRot', dest='vecRotQ', type=str, default='',
+                   help='Rotation quaternion to be applied to the vector to transform it into PAF frame.')
+    p.add_argument('--Hsel', '--selection', type=str, dest='Hseltxt', default='name H', help='Accepted, unused.')
+    p.add_argument('--Xsel', type=str, dest='Xseltxt', default='name N and not resname PRO', help='Accepted, unused.')
+    p.add_argument('--fitsel', type=str, dest='fittxt', default='custom occupancy', help='Accepted, unused.')
+    return p
+
+
+def _load(fn):
+    if fn.endswith('.npy'):
+        return np.load(fn), None, None, None
+    if fn.endswith('.npz'):
+        z = np.load(fn, allow_pickle=True)
+        return (z['vecs'], z['vecs_unfitted'] if 'vecs_unfitted' in z else None,
+                list(z['names']) if 'names' in z else None, float(z['dt']) if 'dt' in z else None)
+    print("= = = ERROR: %s: only .npy/.npz X-H vector trajectories are accepted on this path "
+          "(trajectory reading via mdtraj is out of scope)." % fn, file=sys.stderr)
+    sys.exit(2)
+
+
+def main(argv=None):
+    args = build_parser().parse_args(argv)
+    time_start = time.time()
+    tau_memory = args.tau
+    if args.bDoCt and tau_memory is None:
+        print("= = = Refusing to do C(t)-analysis without using a block averaging over memory_time tau!", file=sys.stderr)
+        sys.exit(1)
+    bDoVecDistrib = args.bDoVecDistrib or args.bDoVecHist
+    histBinX = args.histBin
+    bRotVec = args.vecRotQ != ''
+    q_rot = None
+    if bRotVec:
+        q_rot = np.array([float(v) for v in args.vecRotQ.split()])
+        if len(q_rot) != 4 or not np.allclose(np.dot(q_rot, q_rot), 1):
+            print("= = = ERROR: input rotation quaternion is malformed!", q_rot)
+            sys.exit(23)
+
+    vecXH, vecXHfit, resXH, deltaT = [], [], None, args.dt
+    for fn in args.infn:
+        fit, unfit, names, dt = _load(fn)
+        fit = np.asarray(fit, dtype=np.float32)
+        if fit.ndim != 3 or fit.shape[-1] != 3:
+            print("= = = ERROR: %s does not hold a (frames, bonds, 3) array." % fn, file=sys.stderr)
+            sys.exit(1)
+        print("= = = File loaded - it has %i bonds and %i frames." % (fit.shape[1], fit.shape[0]))
+        if resXH is None:
+            resXH = names if names is not None else list(range(1, fit.shape[1] + 1))
+        elif fit.shape[1] != len(resXH):
+            print("= = = ERROR: Differences in trajectories have been detected! Aborting.", file=sys.stderr)
+            sys.exit(1)
+        if deltaT is None:
+            deltaT = dt
+        vecXHfit.append(fit)
+        vecXH.append(np.asarray(unfit, dtype=np.float32) if unfit is not None else None)
+    if deltaT is None:
+        deltaT = 1.0
+    if tau_memory is not None and deltaT > 0.5 * tau_memory:
+        print("= = = ERROR: delta-t form the trajectory is too small relative to tau! %g vs. %g" % (deltaT, tau_memory),
+              file=sys.stderr)
+        sys.exit(1)
+    print("= = Loading finished.")
+    nBonds = len(resXH)
+    have_ext = all(v is not None for v in vecXH)
+
+    if tau_memory is not None:
+        print("= = Reformatting all vecXH information into chunks of tau ( %g ) " % tau_memory)
+        fit4 = ct.reformat_vecs_by_tau(vecXHfit, deltaT, tau_memory)
+        ext4 = ct.reformat_vecs_by_tau(vecXH, deltaT, tau_memory) if have_ext else None
+    else:
+        cat = np.concatenate(vecXHfit, axis=0)
+        fit4, ext4 = cat[None], None
+
+    if args.bDoCt:
+        dt = ct.calculate_dt(deltaT, tau_memory)
+        if ext4 is not None:
+            print("= = = Conducting Ct_external using Palmer's approach.")
+            Ct, dCt = ct.calculate_Ct_Palmer(ext4)
+            io_formats.print_sxylist(args.out_pref + '_Ctext.dat', resXH, dt, np.stack((Ct.T, dCt.T), axis=-1))
+        print("= = = Conducting Ct_internal using Palmer's approach.")
+        Ct, dCt = ct.calculate_Ct_Palmer(fit4)
+        io_formats.print_sxylist(args.out_pref + '_Ctint.dat', resXH, dt, np.stack((Ct.T, dCt.T), axis=-1))
+
+    sh = fit4.shape
+    frames = fit4.reshape((sh[0] * sh[1], sh[-2], sh[-1]))          # :535-536
+
+    if args.bDoVecAverage:
+        avg = ct.average_vectors(frames, q_rot)
+        io_formats.print_xylist(args.out_pref + '_avgvec.dat', resXH, np.array(avg).T, True)
+
+    if bDoVecDistrib:
+        if not args.bDoVecHist:
+            print("= = = ERROR: only the histogram form of the vector distribution (--vecHist) is produced on this path.",
+                  file=sys.stderr)
+            sys.exit(2)
+        print("= = = Histgrams will use Lambert Cylindrical projection by converting Theta spanning (0,pi) to "
+              "cos(Theta) spanning (-1,1)")
+        hist_list, edges = hist.sphere_histogram(frames, q_rot, histBinX)
+        if args.binary:
+            hist.save_vec_histogram(args.out_pref + '_vecHistogram.npz', resXH, hist_list, edges)
+        else:
+            for i in range(nBonds):
+                ofile = args.out_pref + '_vecXH_' + str(resXH[i]) + '.hist'
+                io_formats.print_gplot_hist(ofile, hist_list[i], edges,
+                                            header='# Lamber Cylindrical Histogram over phi,cos(theta).', bSphere=True)
+                print("= = = Written to output: ", ofile)
+
+    if args.bDoS2:
+        if tau_memory is not None:
+            print("= = = Conducting S2 analysis using memory time to chop input-trajectories", tau_memory, "ps")
+            S2 = ct.calculate_S2_by_outerProduct(frames, deltaT, tau_memory)
+        else:
+            print("= = = Conducting S2 analysis directly from trajectories.")
+            S2 = ct.calculate_S2_by_outerProduct(frames)
+        io_formats.print_xylist(args.out_pref + '_S2.dat', resXH, (S2.T) * args.zeta, True)
+        print("      ...complete.")
+
+    print("= = Finished. Total seconds elapsed: %g" % (time.time() - time_start))
+
+
+if __name__ == '__main__':
+    main()

@@ -13,21 +13,31 @@ namespace {
 // frame per step (static circular indexing, fully unrolled over R), so one step costs
 // 2 LDS.128 + 4R FMA-pipe instructions.
 // ------------------------------------------------------------------------------------------------
-constexpr int kR = 15;         // lags per lane
-constexpr int kMB = 8;         // R-step blocks per warp per frame tile
-constexpr int kFB = 1;         // blocks between FP32 -> FP64 flushes (R*kFB terms per FP32 partial sum)
-constexpr int kNW = 8;         // warps per CTA
-constexpr int kTFW = kR * kMB; // frames per warp per tile
-constexpr int kTF = kNW * kTFW;
-constexpr int kTL = 32 * kR;
-constexpr int kStageVecs = kTF + (kTF + kTL);  // left range + window range, float4 each
-constexpr int kStageBytes = kStageVecs * 16;
-constexpr int kSmemBytes = 2 * kStageBytes;
-static_assert(kMB % kFB == 0, "flush interval must divide the warp tile");
-static_assert(kNW * kTL * 8 <= kSmemBytes, "epilogue reduction buffer must fit in the stage buffers");
+// Tile geometry is a compile-time configuration; kDefaultVariant is what the product launches, the other
+// instantiations exist so that tools/tune_ct.py can time them on the GPU.
+template <int R_, int MB_, int FB_, int NW_, int MINB_>
+struct CtCfg {
+  static constexpr int R = R_;            // lags per lane (odd)
+  static constexpr int MB = MB_;          // R-step blocks per warp per frame tile
+  static constexpr int FB = FB_;          // blocks between FP32 -> FP64 flushes (R*FB terms per FP32 partial sum)
+  static constexpr int NW = NW_;          // warps per CTA
+  static constexpr int MINB = MINB_;      // CTAs per SM promised to the compiler
+  static constexpr int TFW = R * MB;      // frames per warp per tile
+  static constexpr int TF = NW * TFW;     // frames per tile
+  static constexpr int TL = 32 * R;       // lags per tile
+  static constexpr int StageVecs = TF + (TF + TL);   // left range + window range, float4 each
+  static constexpr int StageBytes = StageVecs * 16;
+  static constexpr int SmemBytes = 2 * StageBytes;
+  static_assert(R % 2 == 1, "R must be odd: lane stride of the window LDS.128 has to be conflict free");
+  static_assert(MB % FB == 0, "flush interval must divide the warp tile");
+  static_assert(NW * TL * 8 <= SmemBytes, "epilogue reduction buffer must fit in the stage buffers");
+};
 
-__global__ void __launch_bounds__(kNW * 32, 2)
+template <class Cfg>
+__global__ void __launch_bounds__(Cfg::NW * 32, Cfg::MINB)
 ct_lag_kernel(const float4* __restrict__ U, long long pitch, int nF, int L, int nLT, double* __restrict__ S) {
+  constexpr int kR = Cfg::R, kMB = Cfg::MB, kFB = Cfg::FB, kNW = Cfg::NW, kTFW = Cfg::TFW, kTF = Cfg::TF,
+                kTL = Cfg::TL, kStageVecs = Cfg::StageVecs, kStageBytes = Cfg::StageBytes;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[2];
   float4* const stage_base = reinterpret_cast<float4*>(smem_raw);
@@ -199,12 +209,36 @@ ct_finalize_kernel(const double* __restrict__ S, int nC, int nF, int nR, int L, 
   dCt[(long long)di * nR + r] = (float)(sqrt(var) / (sqrt((double)nC) - 1.0));
 }
 
-}  // namespace
-
 // ================================================================================================
 // C ABI
 // ================================================================================================
-extern "C" long long sr_ct_row_pitch(long long nF) { return sr_round_up(nF + kTF + kTL + 64, 8); }
+// variants (R, MB, FB, NW, CTAs/SM); tools/tune_ct.py times them, kDefaultVariant is the product path
+using CtV0 = CtCfg<15, 8, 1, 8, 2>;
+using CtV1 = CtCfg<15, 8, 2, 8, 2>;
+using CtV2 = CtCfg<15, 8, 4, 8, 2>;
+using CtV3 = CtCfg<15, 8, 2, 8, 1>;
+using CtV4 = CtCfg<15, 8, 2, 12, 1>;
+using CtV5 = CtCfg<13, 8, 2, 8, 2>;
+using CtV6 = CtCfg<17, 8, 2, 8, 2>;
+using CtV7 = CtCfg<15, 12, 2, 8, 2>;
+constexpr int kNumVariants = 8;
+constexpr int kDefaultVariant = 0;   // flush every 15 terms: dCt stays within 1e-5 of the float64 reference
+constexpr int kMaxTF = 1440, kMaxTL = 32 * 17;   // padding must cover the largest tile of any variant
+
+template <class Cfg>
+int launch_ct_lag(const float4* U, long long pitch, long long nF, int nRC, long long L, double* S, cudaStream_t st) {
+  const long long nLT = (L + Cfg::TL - 1) / Cfg::TL;
+  const long long items = (long long)nRC * nLT;
+  SR_REQUIRE(items < (1LL << 31), "sr_ct_lag_sums: %lld work items exceed the grid limit", items);
+  SR_CUDA(cudaFuncSetAttribute(ct_lag_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SmemBytes));
+  ct_lag_kernel<Cfg><<<(unsigned)items, Cfg::NW * 32, Cfg::SmemBytes, st>>>(U, pitch, (int)nF, (int)L, (int)nLT, S);
+  SR_CUDA(cudaGetLastError());
+  return SR_OK;
+}
+
+}  // namespace
+
+extern "C" long long sr_ct_row_pitch(long long nF) { return sr_round_up(nF + kMaxTF + kMaxTL + 64, 8); }
 
 extern "C" size_t sr_ct_workspace_bytes(int nC, long long nF, int nR) {
   const long long pitch = sr_ct_row_pitch(nF);
@@ -236,25 +270,36 @@ extern "C" int sr_pack_vectors_f32(const float* d_vecs, int nC, long long nF, in
   return SR_OK;
 }
 
-extern "C" int sr_ct_lag_sums(const void* d_packed, long long pitch, int nC, long long nF, int nR, long long L,
-                              double* d_S, void* stream) {
+extern "C" int sr_ct_lag_sums_variant(const void* d_packed, long long pitch, int nC, long long nF, int nR, long long L,
+                                      double* d_S, int variant, void* stream) {
   SR_REQUIRE(d_packed && d_S, "sr_ct_lag_sums: null pointer");
   SR_REQUIRE(nC > 0 && nR > 0 && nF >= 2, "sr_ct_lag_sums: bad shape (nC=%d nF=%lld nR=%d)", nC, nF, nR);
   SR_REQUIRE(L >= 1 && L <= nF - 1, "sr_ct_lag_sums: L=%lld outside [1, nF-1]", L);
   SR_REQUIRE(nF < (1LL << 30), "sr_ct_lag_sums: nF too large for 32-bit tile indices");
-  SR_REQUIRE(pitch >= nF + kTF + kTL, "sr_ct_lag_sums: pitch %lld lacks %d frames of zero padding", pitch, kTF + kTL);
-  const long long nLT = (L + kTL - 1) / kTL;
-  const long long items = (long long)nR * nC * nLT;
-  SR_REQUIRE(items < (1LL << 31), "sr_ct_lag_sums: %lld work items exceed the grid limit", items);
-  static bool attr_set = false;
-  if (!attr_set) {
-    SR_CUDA(cudaFuncSetAttribute(ct_lag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    attr_set = true;
+  SR_REQUIRE(pitch >= nF + kMaxTF + kMaxTL, "sr_ct_lag_sums: pitch %lld lacks %d frames of zero padding", pitch,
+             kMaxTF + kMaxTL);
+  SR_REQUIRE((long long)nR * nC < (1LL << 31), "sr_ct_lag_sums: too many (vector, chunk) rows");
+  const float4* U = (const float4*)d_packed;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nRC = nR * nC;
+  switch (variant) {
+    case 0: return launch_ct_lag<CtV0>(U, pitch, nF, nRC, L, d_S, st);
+    case 1: return launch_ct_lag<CtV1>(U, pitch, nF, nRC, L, d_S, st);
+    case 2: return launch_ct_lag<CtV2>(U, pitch, nF, nRC, L, d_S, st);
+    case 3: return launch_ct_lag<CtV3>(U, pitch, nF, nRC, L, d_S, st);
+    case 4: return launch_ct_lag<CtV4>(U, pitch, nF, nRC, L, d_S, st);
+    case 5: return launch_ct_lag<CtV5>(U, pitch, nF, nRC, L, d_S, st);
+    case 6: return launch_ct_lag<CtV6>(U, pitch, nF, nRC, L, d_S, st);
+    case 7: return launch_ct_lag<CtV7>(U, pitch, nF, nRC, L, d_S, st);
+    default: break;
   }
-  ct_lag_kernel<<<(unsigned)items, kNW * 32, kSmemBytes, (cudaStream_t)stream>>>((const float4*)d_packed, pitch, (int)nF,
-                                                                               (int)L, (int)nLT, d_S);
-  SR_CUDA(cudaGetLastError());
-  return SR_OK;
+  sr_set_error("sr_ct_lag_sums_variant: unknown variant %d (have %d)", variant, kNumVariants);
+  return SR_ERR_ARG;
+}
+
+extern "C" int sr_ct_lag_sums(const void* d_packed, long long pitch, int nC, long long nF, int nR, long long L,
+                              double* d_S, void* stream) {
+  return sr_ct_lag_sums_variant(d_packed, pitch, nC, nF, nR, L, d_S, kDefaultVariant, stream);
 }
 
 extern "C" int sr_ct_palmer_finalize(const double* d_S, int nC, long long nF, int nR, long long L, float* d_Ct,

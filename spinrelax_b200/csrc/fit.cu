@@ -143,7 +143,8 @@ ct_fit_lm_kernel(const double* __restrict__ T, const double* __restrict__ Y, con
     double lo = LO[(long long)r * nP + i], hi = HI[(long long)r * nP + i];
     if (i >= nc && i < 2 * nc) lo = fmax(lo, 1e-12 * hi);     // tau strictly positive (SciPy TRF iterates are interior)
     sh.lo[i] = lo; sh.hi[i] = hi;
-    sh.p[i] = fmin(fmax(P0[(long long)r * nP + i], lo), hi);
+    const double eps = 1e-10 * (hi - lo);                     // strictly feasible start (scipy make_strictly_feasible)
+    sh.p[i] = fmin(fmax(P0[(long long)r * nP + i], lo + eps), hi - eps);
   }
   __syncthreads();
   evaluate<nP>(t, y, sig, L, sh.p, sh, sh.JtJ, sh.Jtr, &sh.cost);
@@ -151,14 +152,25 @@ ct_fit_lm_kernel(const double* __restrict__ T, const double* __restrict__ Y, con
   int status = 0, it = 0, small = 0;
   for (; it < max_iter; ++it) {
     if (threadIdx.x == 0) {
+      // active set: a parameter sitting on a bound with the gradient pushing outwards is frozen
       bool fixed[kMaxP];
-      for (int i = 0; i < nP; ++i)
-        fixed[i] = (sh.p[i] <= sh.lo[i] && sh.Jtr[i] > 0.0) || (sh.p[i] >= sh.hi[i] && sh.Jtr[i] < 0.0);
+      for (int i = 0; i < nP; ++i) {
+        const double span = sh.hi[i] - sh.lo[i];
+        const bool at_lo = sh.p[i] - sh.lo[i] <= 1e-12 * span, at_hi = sh.hi[i] - sh.p[i] <= 1e-12 * span;
+        fixed[i] = (at_lo && sh.Jtr[i] > 0.0) || (at_hi && sh.Jtr[i] < 0.0);
+      }
       double d[kMaxP];
       int ok = lm_step(sh.JtJ, sh.Jtr, fixed, nP, lam, d) ? 1 : 0;
+      // fraction-to-boundary rule: the trial point stays strictly inside the box (as SciPy's TRF iterates do),
+      // so a wild step can never park tau on 0 where the model has no gradient
+      double alpha = 1.0;
+      for (int i = 0; i < nP; ++i) {
+        if (d[i] < 0.0) alpha = fmin(alpha, 0.995 * (sh.p[i] - sh.lo[i]) / (-d[i]));
+        else if (d[i] > 0.0) alpha = fmin(alpha, 0.995 * (sh.hi[i] - sh.p[i]) / d[i]);
+      }
       double smax = 0.0;
       for (int i = 0; i < nP; ++i) {
-        const double q = fmin(fmax(sh.p[i] + d[i], sh.lo[i]), sh.hi[i]);
+        const double q = fmin(fmax(sh.p[i] + alpha * d[i], sh.lo[i]), sh.hi[i]);
         smax = fmax(smax, fabs(q - sh.p[i]) / (fabs(sh.p[i]) + 1e-300));
         sh.ptry[i] = q;
       }
@@ -181,8 +193,10 @@ ct_fit_lm_kernel(const double* __restrict__ T, const double* __restrict__ Y, con
       }
       lam = fmax(lam * 0.3, 1e-12);
       __syncthreads();
-      small = (c0 - c1 <= ftol * c0) ? small + 1 : 0;      // three consecutive negligible decreases = converged
-      if (small >= 3) { status = 1; ++it; break; }
+      // converged: three consecutive negligible decreases taken with (almost) undamped Gauss-Newton steps.
+      // A tiny decrease under heavy damping only means the step was short (flat multi-exponential valleys).
+      small = (c0 - c1 <= ftol * c0) ? small + 1 : 0;
+      if (small >= 3 && lam <= 1e-7) { status = 1; ++it; break; }
     } else {
       lam *= 4.0;
       if (lam > 1e20) { status = 3; break; }

@@ -11,16 +11,21 @@
 
 namespace {
 
-constexpr int kHistThreads = 256;
+constexpr int kHistThreads = 512;
 
 struct HistParams {
   double R[9];        // rotation matrix (row major), identity when no rotation
-  double tol_phi;     // angular margin (rad)
-  double tol_cos;     // cos(theta) margin
+  double tol_phi;     // angular margin (rad) of the FP64 test
+  double tol_cos;     // cos(theta) margin of the FP64 test
+  float Rf[9];        // the same matrix in float32 for the fast path
+  float fphi_abs, fphi_rel, fcos;   // fast-path margins (see fast_classify)
   int nbx, nby;
+  int f32_reference;  // 1: no rotation, the reference itself works in float32 -> fast-path misses go to the host
 };
 
-__device__ __forceinline__ int classify(double x, double y, double z, const HistParams& p,
+struct SlowParams { double tol_phi, tol_cos; int nbx, nby; };
+
+__device__ __forceinline__ int classify(double x, double y, double z, const SlowParams p,
                                         const double2* __restrict__ edge_dir,   // (cos e_i, sin e_i), i = 0..nbx
                                         const double* __restrict__ edge_cos,    // e_j, j = 0..nby
                                         int& bin_out) {
@@ -66,68 +71,159 @@ __device__ __forceinline__ int classify(double x, double y, double z, const Hist
   return 0;
 }
 
-// grid.x = vector groups (fastest, so CTAs sharing a frame range run together and the 64-byte DRAM
-// blocks that straddle two groups are fetched once), grid.y = frame blocks.  `group` = 1 << gshift vectors
-// per CTA; bins are privatised in shared memory as packed 16-bit counters (a CTA sees < 65536 frames).
-__global__ void __launch_bounds__(kHistThreads)
+// FP32 fast path.  Returns the flat bin, or -1 when the sample is within the fast-path margin of a bin edge
+// (or degenerate) and has to be re-examined.  The margin covers the float32 rounding of the rotated
+// coordinates (fphi_abs, absolute, rotated path) or the reference's own float32 arctan2/arccos/cos error
+// (fphi_rel, relative to the xy-projection, unrotated path).
+struct FastParams { float fphi_abs, fphi_rel, fcos; int nbx, nby; };
+
+__device__ __forceinline__ int fast_classify(float x, float y, float z, const FastParams p,
+                                             const float4* __restrict__ sh_edge /* (cos_i, sin_i, cos_i+1, sin_i+1) */) {
+  // NaN, zero, huge or polar vectors need no explicit test: they fail the margin comparisons below
+  // (rsqrtf(0) = inf -> cf = NaN; rho1 = 0 -> |cross| = 0 < mphi) and drop to the slow path.
+  const float r2 = fmaf(x, x, fmaf(y, y, z * z));
+  const float ax = fabsf(x), ay = fabsf(y);
+  const float rho1 = ax + ay;
+  // phi candidate from a degree-11 odd minimax polynomial of atan on [0,1] (max error 1.8e-6 rad)
+  const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+  const float t = __fdividef(mn, mx), t2 = t * t;
+  float a = fmaf(t2, -0.01171912346035242f, 0.052647337317466736f);
+  a = fmaf(t2, a, -0.1164264902472496f);
+  a = fmaf(t2, a, 0.19354039430618286f);
+  a = fmaf(t2, a, -0.33262282609939575f);
+  a = fmaf(t2, a, 0.9999772310256958f) * t;
+  if (ay > ax) a = 1.57079632679f - a;
+  if (x < 0.f) a = 3.14159265359f - a;
+  if (y < 0.f) a = -a;
+  int i = (int)floorf((a + 3.14159265359f) * (p.nbx * 0.159154943f));
+  i = max(0, min(p.nbx - 1, i));
+  const float4 e = sh_edge[i];
+  const float mphi = fmaf(p.fphi_rel, rho1, p.fphi_abs * (rho1 + fabsf(z))) + 1e-30f;
+  const float clo = fmaf(e.x, y, -e.y * x);   // rho sin(phi - e_i)
+  const float chi = fmaf(e.z, y, -e.w * x);   // rho sin(phi - e_{i+1})
+  const bool ok_phi = (clo >= mphi) && (chi <= -mphi);
+  // cos(theta)
+  const float cf = z * rsqrtf(r2);
+  const float wbin = 2.0f / p.nby;
+  int j = (int)floorf((cf + 1.0f) * (0.5f * p.nby));
+  j = max(0, min(p.nby - 1, j));
+  const float elo = fmaf((float)j, wbin, -1.0f), ehi = elo + wbin;
+  const bool ok_cos = (cf - elo >= p.fcos) && (ehi - cf >= p.fcos);   // NaN compares false
+  return (ok_phi && ok_cos) ? i * p.nby + j : -1;
+}
+
+// Rare path, kept out of line so the hot loop stays small: FP64 re-examination (rotated stream) or hand-over
+// to the host (float32 reference stream), NaN / zero vectors dropped as np.histogramdd drops them.
+__device__ __noinline__ void slow_sample(float vx, float vy, float vz, int f32_reference, double r0, double r1, double r2,
+                                         double r3, double r4, double r5, double r6, double r7, double r8,
+                                         double tol_phi, double tol_cos, int nbx, int nby,
+                                         const double2* __restrict__ edge_dir, const double* __restrict__ edge_cos,
+                                         unsigned int* sh_vec_hist, long long sample_idx, long long* __restrict__ amb_idx,
+                                         int amb_capacity, int* __restrict__ amb_count) {
+  int bin = 0, cls;
+  if (f32_reference) {
+    const float n2 = vx * vx + vy * vy + vz * vz;
+    cls = (n2 != n2 || n2 == 0.f) ? 1 : 2;
+  } else {
+    const double dx = vx, dy = vy, dz = vz;
+    SlowParams sp; sp.tol_phi = tol_phi; sp.tol_cos = tol_cos; sp.nbx = nbx; sp.nby = nby;
+    cls = classify(r0 * dx + r1 * dy + r2 * dz, r3 * dx + r4 * dy + r5 * dz, r6 * dx + r7 * dy + r8 * dz, sp, edge_dir,
+                   edge_cos, bin);
+  }
+  if (cls == 0) {
+    atomicAdd(&sh_vec_hist[bin >> 1], 1u << ((bin & 1) << 4));
+  } else if (cls == 2) {
+    const int slot = atomicAdd(amb_count, 1);
+    if (slot < amb_capacity) amb_idx[slot] = sample_idx;
+  }
+}
+
+constexpr int kHistU = 4;
+
+// grid.x = vector groups (fastest, so CTAs sharing a frame range run together and the 64-byte DRAM blocks
+// that straddle two groups are fetched once), grid.y = frame blocks.  A CTA owns `group` = 1 << gshift
+// vectors; thread t always works on vector t & (group-1), so its shared-memory histogram base and its global
+// pointer stride are loop invariants.  Bins are privatised in shared memory as packed 16-bit counters
+// (an even number of bins per vector; a CTA sees < 65536 frames).
+__global__ void __launch_bounds__(kHistThreads, 2)
 sphere_hist_kernel(const float* __restrict__ vecs, long long nFrames, int nR, int gshift, int framesPerBlock,
                    HistParams p, const double2* __restrict__ edge_dir, const double* __restrict__ edge_cos,
                    unsigned int* __restrict__ counts, long long* __restrict__ amb_idx, int amb_capacity,
                    int* __restrict__ amb_count) {
-  extern __shared__ unsigned int sh_hist[];
+  extern __shared__ unsigned int sh_raw[];
+  float4* sh_edge = reinterpret_cast<float4*>(sh_raw);
+  unsigned int* sh_hist = sh_raw + 4 * p.nbx;
   const int nbins = p.nbx * p.nby;
+  const int wordsPerVec = (nbins + 1) >> 1;
   const int group = 1 << gshift;
   const int r0 = blockIdx.x * group;
   const int nv = min(group, nR - r0);
-  const int nwords = (nv * nbins + 1) >> 1;
-  for (int i = threadIdx.x; i < nwords; i += kHistThreads) sh_hist[i] = 0u;
+  for (int i = threadIdx.x; i < nv * wordsPerVec; i += kHistThreads) sh_hist[i] = 0u;
+  for (int i = threadIdx.x; i < p.nbx; i += kHistThreads) {
+    const double2 lo = edge_dir[i], hi = edge_dir[i + 1];
+    sh_edge[i] = make_float4((float)lo.x, (float)lo.y, (float)hi.x, (float)hi.y);
+  }
   __syncthreads();
 
   const long long f0 = (long long)blockIdx.y * framesPerBlock;
   const int nfl = (int)min((long long)framesPerBlock, nFrames - f0);
-  const int nSamp = nfl << gshift;
-  const float* base = vecs + (f0 * nR + r0) * 3;
-  const int rowStride = nR * 3;
-  constexpr int U = 4;
-  for (int s0 = threadIdx.x; s0 < nSamp; s0 += kHistThreads * U) {
-    float vx[U], vy[U], vz[U];
-    bool on[U];
+  const int vl = threadIdx.x & (group - 1);
+  const int FP = kHistThreads >> gshift;          // frames covered by one pass of the CTA
+  const size_t rowStride = (size_t)nR * 3;
+  if (vl < nv) {
+    unsigned int* const myhist = sh_hist + vl * wordsPerVec;
+    const long long sidx0 = f0 * nR + r0 + vl;
+    int fl = threadIdx.x >> gshift;
+    const float* src = vecs + ((size_t)(f0 + fl) * nR + r0 + vl) * 3;
+    FastParams fp;
+    fp.fphi_abs = p.fphi_abs; fp.fphi_rel = p.fphi_rel; fp.fcos = p.fcos; fp.nbx = p.nbx; fp.nby = p.nby;
+    const float q0 = p.Rf[0], q1 = p.Rf[1], q2 = p.Rf[2], q3 = p.Rf[3], q4 = p.Rf[4], q5 = p.Rf[5], q6 = p.Rf[6],
+                q7 = p.Rf[7], q8 = p.Rf[8];
+    auto fast = [&](float vx, float vy, float vz) {
+      const float x = fmaf(q0, vx, fmaf(q1, vy, q2 * vz));
+      const float y = fmaf(q3, vx, fmaf(q4, vy, q5 * vz));
+      const float z = fmaf(q6, vx, fmaf(q7, vy, q8 * vz));
+      return fast_classify(x, y, z, fp, sh_edge);
+    };
+    for (; fl + (kHistU - 1) * FP < nfl; fl += kHistU * FP, src += (size_t)kHistU * FP * rowStride) {
+      float vx[kHistU], vy[kHistU], vz[kHistU];
+      int bin[kHistU];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int s = s0 + u * kHistThreads;
-      const int vl = s & (group - 1), fl = s >> gshift;
-      on[u] = (s < nSamp) && (vl < nv);
-      vx[u] = vy[u] = vz[u] = 0.f;
-      if (on[u]) {
-        const float* src = base + (long long)fl * rowStride + vl * 3;
-        vx[u] = __ldg(src); vy[u] = __ldg(src + 1); vz[u] = __ldg(src + 2);
+      for (int u = 0; u < kHistU; ++u) {
+        const float* s2 = src + (size_t)u * FP * rowStride;
+        vx[u] = __ldg(s2); vy[u] = __ldg(s2 + 1); vz[u] = __ldg(s2 + 2);
+      }
+      int worst = 0;
+#pragma unroll
+      for (int u = 0; u < kHistU; ++u) { bin[u] = fast(vx[u], vy[u], vz[u]); worst = min(worst, bin[u]); }
+#pragma unroll
+      for (int u = 0; u < kHistU; ++u)
+        if (bin[u] >= 0) atomicAdd(&myhist[bin[u] >> 1], 1u << ((bin[u] & 1) << 4));
+      if (worst < 0) {
+#pragma unroll 1
+        for (int u = 0; u < kHistU; ++u)
+          if (bin[u] < 0)
+            slow_sample(vx[u], vy[u], vz[u], p.f32_reference, p.R[0], p.R[1], p.R[2], p.R[3], p.R[4], p.R[5], p.R[6], p.R[7],
+                        p.R[8], p.tol_phi, p.tol_cos, p.nbx, p.nby, edge_dir, edge_cos, myhist,
+                        sidx0 + (long long)(fl + u * FP) * nR, amb_idx, amb_capacity, amb_count);
       }
     }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (!on[u]) continue;
-      const int s = s0 + u * kHistThreads;
-      const int vl = s & (group - 1), fl = s >> gshift;
-      const double dx = vx[u], dy = vy[u], dz = vz[u];
-      const double x = p.R[0] * dx + p.R[1] * dy + p.R[2] * dz;
-      const double y = p.R[3] * dx + p.R[4] * dy + p.R[5] * dz;
-      const double z = p.R[6] * dx + p.R[7] * dy + p.R[8] * dz;
-      int bin = 0;
-      const int cls = classify(x, y, z, p, edge_dir, edge_cos, bin);
-      if (cls == 0) {
-        const int k = vl * nbins + bin;
-        atomicAdd(&sh_hist[k >> 1], 1u << ((k & 1) << 4));
-      } else if (cls == 2) {
-        const int slot = atomicAdd(amb_count, 1);
-        if (slot < amb_capacity) amb_idx[slot] = (f0 + fl) * nR + r0 + vl;
-      }
+    for (; fl < nfl; fl += FP, src += (size_t)FP * rowStride) {
+      const float vx = __ldg(src), vy = __ldg(src + 1), vz = __ldg(src + 2);
+      const int bin = fast(vx, vy, vz);
+      if (bin >= 0) atomicAdd(&myhist[bin >> 1], 1u << ((bin & 1) << 4));
+      else slow_sample(vx, vy, vz, p.f32_reference, p.R[0], p.R[1], p.R[2], p.R[3], p.R[4], p.R[5], p.R[6], p.R[7], p.R[8],
+                       p.tol_phi, p.tol_cos, p.nbx, p.nby, edge_dir, edge_cos, myhist, sidx0 + (long long)fl * nR, amb_idx,
+                       amb_capacity, amb_count);
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < nwords; i += kHistThreads) {
+  for (int i = threadIdx.x; i < nv * wordsPerVec; i += kHistThreads) {
     const unsigned int w = sh_hist[i];
-    if (w & 0xffffu) atomicAdd(&counts[(long long)r0 * nbins + 2 * i], w & 0xffffu);
-    if (w >> 16) atomicAdd(&counts[(long long)r0 * nbins + 2 * i + 1], w >> 16);
+    const int v = i / wordsPerVec, k = i - v * wordsPerVec;
+    const long long g = (long long)(r0 + v) * nbins + 2 * k;
+    if (w & 0xffffu) atomicAdd(&counts[g], w & 0xffffu);
+    if (w >> 16) atomicAdd(&counts[g + 1], w >> 16);
   }
 }
 
@@ -156,6 +252,13 @@ extern "C" int sr_sphere_hist(const float* d_vecs, long long nFrames, int nR, co
     p.R[3] = 2 * (x * y + w * z);     p.R[4] = 1 - 2 * (x * x + z * z); p.R[5] = 2 * (y * z - w * x);
     p.R[6] = 2 * (x * z - w * y);     p.R[7] = 2 * (y * z + w * x);     p.R[8] = 1 - 2 * (x * x + y * y);
   }
+  for (int i = 0; i < 9; ++i) p.Rf[i] = (float)p.R[i];
+  p.f32_reference = h_q_rot ? 0 : 1;
+  if (h_q_rot) {   // float32 rounding of the rotated coordinates: ~3e-7 |v| absolute
+    p.fphi_abs = 1.5e-6f; p.fphi_rel = 0.f; p.fcos = 2.0e-6f;
+  } else {         // the caller's tolerances describe the reference's own float32 error
+    p.fphi_abs = 1e-12f; p.fphi_rel = (float)tol_phi; p.fcos = (float)tol_cos;
+  }
   const int nbins = nbx * nby;
   int dev = 0, max_smem = 0, sms = 0;
   SR_CUDA(cudaGetDevice(&dev));
@@ -163,10 +266,11 @@ extern "C" int sr_sphere_hist(const float* d_vecs, long long nFrames, int nR, co
   SR_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   // two CTAs per SM: at most ~100 KB of privatised 16-bit bins each; group is a power of two <= 16
   int gshift = 4;
-  while (gshift > 0 && (((size_t)(1 << gshift) * nbins + 1) / 2) * 4 > (size_t)100 * 1024) --gshift;
+  const size_t wordsPerVec = ((size_t)nbins + 1) / 2;
+  while (gshift > 0 && ((size_t)(1 << gshift) * wordsPerVec) * 4 > (size_t)100 * 1024) --gshift;
   while (gshift > 0 && (1 << (gshift - 1)) >= nR) --gshift;
   const int group = 1 << gshift;
-  const size_t smem = (((size_t)group * nbins + 1) / 2) * 4;
+  const size_t smem = (size_t)group * wordsPerVec * 4 + (size_t)nbx * 16;
   SR_REQUIRE(smem <= (size_t)max_smem, "sr_sphere_hist: %d bins do not fit in shared memory", nbins);
   SR_CUDA(cudaFuncSetAttribute(sphere_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int nGroups = (nR + group - 1) / group;
@@ -216,6 +320,64 @@ extern "C" int sr_rotate_vectors_f32_f64(const float* d_v, long long n, const do
   SR_REQUIRE(n >= 1, "sr_rotate_vectors_f32_f64: empty input");
   rotate_f32_f64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_v, n, h_q[0], h_q[1], h_q[2],
                                                                                      h_q[3], d_out);
+  SR_CUDA(cudaGetLastError());
+  return SR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// First and second moments of the bond vectors per (block of frames, vector): the reductions behind
+// --vecAvg (calculate-Ct-from-traj.py:579-583) and --S2 (calculate_S2_by_outerProduct :96-145), which
+// run-all.bash:481 always requests together with --Ct.  out[block][r][9] = sum x,y,z,xx,xy,xz,yy,yz,zz (FP64).
+// ------------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256)
+vec_block_moments_kernel(const float* __restrict__ vecs, long long nFrames, int nR, long long framesPerBlock,
+                         int tilesPerBlock, double* __restrict__ out) {
+  // grid.x = vector groups of 16, grid.y = block * tilesPerBlock + tile
+  __shared__ double red[9][256];
+  const int r0 = blockIdx.x * 16;
+  const int vl = threadIdx.x & 15, fsub = threadIdx.x >> 4;       // 16 frames per pass
+  const long long blk = blockIdx.y / tilesPerBlock;
+  const int tile = blockIdx.y - (int)blk * tilesPerBlock;
+  const long long tileLen = (framesPerBlock + tilesPerBlock - 1) / tilesPerBlock;
+  const long long fa = blk * framesPerBlock + (long long)tile * tileLen;
+  const long long fb = min(min(nFrames, (blk + 1) * framesPerBlock), fa + tileLen);
+  double s[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  if (r0 + vl < nR) {
+    for (long long f = fa + fsub; f < fb; f += 16) {
+      const float* src = vecs + (f * nR + r0 + vl) * 3;
+      const double x = __ldg(src), y = __ldg(src + 1), z = __ldg(src + 2);
+      s[0] += x; s[1] += y; s[2] += z;
+      s[3] = fma(x, x, s[3]); s[4] = fma(x, y, s[4]); s[5] = fma(x, z, s[5]);
+      s[6] = fma(y, y, s[6]); s[7] = fma(y, z, s[7]); s[8] = fma(z, z, s[8]);
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < 9; ++m) red[m][threadIdx.x] = s[m];
+  __syncthreads();
+  if (threadIdx.x < 16 * 9) {
+    const int v = threadIdx.x & 15, m = threadIdx.x >> 4;
+    double t = 0.0;
+    for (int k = 0; k < 16; ++k) t += red[m][k * 16 + v];
+    if (r0 + v < nR) atomicAdd(&out[(blk * nR + r0 + v) * 9 + m], t);
+  }
+}
+}  // namespace
+
+extern "C" int sr_vec_block_moments(const float* d_vecs, long long nFrames, int nR, long long framesPerBlock,
+                                    double* d_out, void* stream) {
+  SR_REQUIRE(d_vecs && d_out, "sr_vec_block_moments: null pointer");
+  SR_REQUIRE(nFrames > 0 && nR > 0 && framesPerBlock > 0, "sr_vec_block_moments: empty shape");
+  const long long nBlocks = (nFrames + framesPerBlock - 1) / framesPerBlock;
+  const int groups = (nR + 15) / 16;
+  long long tiles = (2048 + groups * nBlocks - 1) / (groups * nBlocks);       // ~2048 CTAs in flight
+  const long long maxTiles = (framesPerBlock + 255) / 256;
+  if (tiles > maxTiles) tiles = maxTiles;
+  if (tiles < 1) tiles = 1;
+  SR_REQUIRE(nBlocks * tiles <= 65535, "sr_vec_block_moments: too many frame blocks");
+  SR_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double) * 9 * (size_t)nBlocks * nR, (cudaStream_t)stream));
+  dim3 grid((unsigned)groups, (unsigned)(nBlocks * tiles));
+  vec_block_moments_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_vecs, nFrames, nR, framesPerBlock, (int)tiles, d_out);
   SR_CUDA(cudaGetLastError());
   return SR_OK;
 }

@@ -123,3 +123,57 @@ def calculate_Ct_Palmer(vecs, _verbose=True):
                                Ct.ctypes.data_as(ctypes.c_void_p), dCt.ctypes.data_as(ctypes.c_void_p))
     _lib.check(rc, "sr_ct_palmer_host")
     return Ct.astype(out_dtype, copy=False), dCt.astype(out_dtype, copy=False)
+
+
+def _block_moments(vecs3, frames_per_block):
+    """GPU sums of x,y,z and the six second moments per (block, vector): (nBlocks, nR, 9) float64."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    v = np.ascontiguousarray(vecs3, dtype=np.float32)
+    nFr, nR, _ = v.shape
+    nB = -(-nFr // frames_per_block)
+    vd = torch.from_numpy(v).cuda()
+    out = torch.empty((nB, nR, 9), dtype=torch.float64, device=vd.device)
+    _lib.check(lib.sr_vec_block_moments(vd.data_ptr(), nFr, nR, int(frames_per_block), out.data_ptr(),
+                                        _lib.current_stream_ptr()), "sr_vec_block_moments")
+    return out.cpu().numpy()
+
+
+def _s2_from_moments(m, n):
+    """1.5 sum_ij <v_i v_j>^2 - 0.5 from packed (xx,xy,xz,yy,yz,zz) sums over n frames."""
+    a = m / n
+    return 1.5 * (a[..., 0] ** 2 + a[..., 3] ** 2 + a[..., 5] ** 2
+                  + 2.0 * (a[..., 1] ** 2 + a[..., 2] ** 2 + a[..., 4] ** 2)) - 0.5
+
+
+def calculate_S2_by_outerProduct(vecs, delta_t=-1, tau_memory=-1):
+    """Order parameter S2 = 3/2 sum_ij <e_i e_j>^2 - 1/2 (calculate-Ct-from-traj.py:96-145) for (frames, nR, 3)
+    or (frames, 3) vectors; with delta_t and tau_memory the mean and std/(sqrt(nBlocks)-1) over tau-long blocks."""
+    vecs = np.asarray(vecs)
+    single = (vecs.ndim == 2)
+    v3 = vecs[:, None, :] if single else vecs
+    if v3.ndim != 3:
+        print("= = = ERROR in calculate_S2_by_outerProduct: unsupported number of dimensions! vecs.shape: ",
+              vecs.shape, file=sys.stderr)
+        sys.exit(1)
+    nFr = v3.shape[0]
+    if delta_t < 0 or tau_memory < 0:
+        s2 = _s2_from_moments(_block_moments(v3, nFr)[0, :, 3:], nFr)
+        return s2[0] if single else s2
+    per = int(tau_memory / delta_t)
+    nB = int(nFr / per)
+    m = _block_moments(v3[: nB * per], per)[:, :, 3:]
+    s2 = _s2_from_moments(m, per)
+    out = np.stack((s2.mean(axis=0), s2.std(axis=0) / (np.sqrt(nB) - 1.0)), axis=-1)
+    return out[0] if single else out
+
+
+def average_vectors(vecs3, q_rot=None):
+    """--vecAvg (:579-583): normalised mean vector per bond, optionally in the PAF frame.  The mean of the
+    rotated vectors is the rotated mean, so only the (nR, 3) sums leave the GPU."""
+    from . import qs
+    v3 = np.asarray(vecs3)
+    mean = _block_moments(v3, v3.shape[0])[0, :, :3] / v3.shape[0]
+    if q_rot is not None:
+        mean = qs.rotate_vector_simd(mean, np.asarray(q_rot, dtype=np.float64))
+    return mean / np.linalg.norm(mean, axis=-1, keepdims=True)

@@ -371,8 +371,10 @@ class autoCorrelations:
                 s += 2
 
     # -- batched ladder: one kernel launch per rung for all residues still climbing --
-    def fit_all_residues(self, listDoG=(2, 3, 5, 7, 9), chiSqThreshold=0.5, fp=sys.stdout):
-        """calculate-fitted-Ct.py:162-178 for every target at once.  Adds/overwrites one model per target key."""
+    def fit_all_residues(self, listDoG=(2, 3, 5, 7, 9), chiSqThreshold=0.5, fp=sys.stdout, single=False):
+        """calculate-fitted-Ct.py:162-178 for every target at once.  Adds/overwrites one model per target key.
+        single=True reproduces the fixed-parameter-count branch (:174-178): one conduct_curve_fitting per residue,
+        result kept whatever its quality flags."""
         keys = list(self.DeltaT.keys())
         L = {len(self.DeltaT[k]) for k in keys}
         if len(L) != 1:
@@ -407,6 +409,10 @@ class autoCorrelations:
                 else:
                     chiSq, bQ = m._absorb_fit(popt[j], pcov[j], T[i], Y[i], None if SG is None else SG[i], fp)
                 print("    ...%s: fit with %i params yield chiSq of %g" % (m.name, nParams, chiSq), file=fp)
+                if single:
+                    prev[k].copy_from(m)
+                    first[k] = False
+                    continue
                 if first[k]:
                     if np.all(bQ):
                         prev[k].copy_from(m)

@@ -111,3 +111,40 @@ def load_sxydylist(fn, key="legend"):
     if dys != []:
         return legs, np.array(xs), np.array(ys), np.array(dys)
     return legs, np.array(xs), np.array(ys), []
+
+
+def print_gplot_hist(fn, hist, edges, header='', bSphere=False):
+    """Gnuplot text form of a histogram, bin centres (general_scripts.py:327-381).  With bSphere the 2-D
+    (phi, cos theta) map is closed: pole caps at the first/last cos(theta) edge and a repeat of the first phi
+    row at +2 pi."""
+    nb = hist.shape
+    dim = len(nb)
+    ctr = [0.5 * (np.asarray(edges[i])[:-1] + np.asarray(edges[i])[1:]) for i in range(dim)]
+    with open(fn, 'w') as fp:
+        if header != '':
+            print('%s' % header, file=fp)
+        print('# DIMENSIONS: %i' % dim, file=fp)
+        print("# BINWIDTH: " + " ".join("%g" % ((edges[i][-1] - edges[i][0]) / nb[i]) for i in range(dim)), file=fp)
+        print("# NBINS: " + " ".join("%g" % (nb[i]) for i in range(dim)), file=fp)
+        if not bSphere:
+            for index, val in np.ndenumerate(hist):
+                print(" ".join("%g" % ctr[i][index[i]] for i in range(dim)) + " %g" % val, file=fp)
+                if index[-1] == nb[-1] - 1:
+                    print('', file=fp)
+            return
+        if dim != 2:
+            import sys
+            print("= = = ERROR: histogram data is not in 2D, but spherical histogram plotting is requested!", file=sys.stderr)
+            sys.exit(1)
+        ymin, ymax = edges[1][0], edges[1][-1]
+
+        def row(x, h):
+            print('%g %g %g' % (x, ymin, h[0]), file=fp)
+            for j in range(nb[1]):
+                print('%g %g %g' % (x, ctr[1][j], h[j]), file=fp)
+            print('%g %g %g' % (x, ymax, h[-1]), file=fp)
+            print('', file=fp)
+
+        for i in range(nb[0]):
+            row(ctr[0][i], hist[i])
+        row(ctr[0][0] + 2 * np.pi, hist[0])

@@ -31,8 +31,6 @@ class CtHistStep:
         if self.has_hist:
             from . import hist as _hist
             self._hist = _hist.SphereHistogram(nR, self.nbx, device=self.dev)
-        if world > 1 and rank == 0:
-            self.gathered = [torch.empty((2, self.L, nR), dtype=torch.float32, device=self.dev) for _ in range(world)]
         self._events = {}
         self._launches = 3 + (1 if self.has_hist else 0)
 
@@ -67,9 +65,10 @@ class CtHistStep:
                         time_kernels)
             hist = self._hist.finish(v_dev, self.q_rot)     # ambiguous-sample tie-break + D2H of the counts
         if self.world > 1:
-            import torch.distributed as dist
-            mine = self.torch.stack((self.Ct, self.dCt))
-            dist.gather(mine, self.gathered if self.rank == 0 else None, dst=0)
+            # every rank owns nR vectors of the global set: gather the (2L, nR) result columns on rank 0
+            from . import shard
+            both = self.torch.cat((self.Ct, self.dCt), dim=0)
+            self.gathered = shard.gather_columns(both, self.nR * self.world, dst=0)
         return self.Ct, self.dCt, hist
 
     def run_host(self, v_np):

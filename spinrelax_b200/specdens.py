@@ -517,3 +517,123 @@ class spinRelaxationR2(spinRelaxationBase):
 
 class spinRelaxationNOE(spinRelaxationBase):
     _col = 2
+
+
+class spinRelaxationExperiments:
+    """Container for several experiments sharing one tumbling model and one set of C(t) models
+    (spectral_densities.py:909-1420).  Reproduced: add_experiment (:935-1010), set_global_zeta, eval_all (:1145-1150),
+    initialise_CSA_array, export_xvg (:1178-1194).  The Powell optimisers over Diso / Daniso / zeta / CSA / rsCSA
+    (:1302-1447) are not part of this path; the CSA grids they generate are served by `relax_grid`."""
+
+    def __init__(self, globalRotDif=None, localCtModels=None):
+        self.numExpts = 0
+        self.spinrelax = []
+        self.data = []
+        self.globalRotDif = globalRotDif
+        self.localCtModels = localCtModels
+
+    def add_experiment(self, fileName, bIgnoreErrors=False):
+        strType = nucleiA = nucleiB = freq = None
+        freqUnit = 'MHz'
+        names, values, errors = [], [], []
+        for line in open(fileName, 'r'):
+            l = line.split()
+            if len(l) == 0:
+                continue
+            if line[0] in '#@':
+                if len(l) > 2:
+                    key = l[1]
+                    if key == 'Type':
+                        strType = l[2]
+                    elif key == 'NucleiA':
+                        nucleiA = l[2]
+                    elif key == 'NucleiB':
+                        nucleiB = l[2]
+                    elif key == 'Frequency':
+                        freq = float(l[2])
+                    elif key == 'FrequencyUnit':
+                        freqUnit = l[2]
+                continue
+            if len(l) == 1 or len(l) > 3:
+                print("ERROR in spinRelaxationExperiments.add_experiment(): data line does not obey expected "
+                      "conventions of 2 or 3 space-separated values!", l, file=sys.stderr)
+                sys.exit()
+            names.append(l[0])
+            values.append(float(l[1]))
+            errors.append(float(l[2]) if len(l) > 2 else None)
+        if nucleiB is None and strType in ('R1', 'R2'):
+            nucleiB = '1H'
+        if strType is None or nucleiA is None or nucleiB is None or freq is None:
+            print("ERROR in spinRelaxationExperiments.add_experiment(): not all metadata has been read! "
+                  "Require: Type, NucleiA, NucleiB, Frequency", file=sys.stderr)
+            sys.exit(1)
+        nMissing = sum(x is None for x in errors)
+        if nMissing == len(errors):
+            errors = None
+        elif nMissing > 0:
+            print("ERROR in spinRelaxationExperiments.add_experiment(): either all entries must have uncertainties "
+                  "or none!", file=sys.stderr)
+            sys.exit(1)
+        wObj = angularFrequencies(nucleiA=nucleiA, nucleiB=nucleiB, fieldStrength=freq, fieldUnit=freqUnit)
+        cls = {'R1': spinRelaxationR1, 'R2': spinRelaxationR2, 'NOE': spinRelaxationNOE}[strType]
+        self.spinrelax.append(cls(strType, angFreq=wObj, globalRotDif=self.globalRotDif, localCtModels=self.localCtModels))
+        self.data.append(dict(names=np.array(names), y=np.array(values, dtype=float), dy=errors))
+        self.numExpts += 1
+
+    def set_global_zeta(self, zeta):
+        self.localCtModels.set_zeta(zeta)
+
+    def get_zeta(self):
+        return self.localCtModels.get_zeta()
+
+    def get_first_csa(self):
+        return self.spinrelax[0].angFreq.gA.csa
+
+    def initialise_CSA_array(self, namesCSA, CSAValues):
+        namesCSA = [str(x) for x in namesCSA]
+        namesCt = [str(x) for x in self.localCtModels.get_names()]
+        default = self.get_first_csa()
+        vals = [CSAValues[namesCSA.index(n)] if n in namesCSA else default for n in namesCt]
+        for sp in self.spinrelax:
+            sp.angFreq.initialise_CSA_array(len(vals), vals)
+
+    def eval_all(self, ind=None, bVerbose=False):
+        for sp in self.spinrelax:
+            if bVerbose:
+                print('...evaluating experiment %s at %g T.' % (sp.name, sp.angFreq.B0))
+            sp.eval(ind=ind, bVerbose=bVerbose)
+
+    def get_all_values(self, ind=None):
+        out = []
+        for sp in self.spinrelax:
+            v, e = sp.get_values(ind=ind), sp.get_errors(ind=ind)
+            out.append([v, e] if e is not None else [v])
+        return out
+
+    def print_parameters(self, style='stdout', fp=sys.stdout):
+        """`# Fixed <name>: <value> <unit>` lines of the .xvg header (:1224-1242; nothing is optimised here)."""
+        csa = self.get_first_csa()
+        rows = (('Diso', self.globalRotDif.get_Diso(), 'ps^-1', 'Fixed'),
+                ('Daniso', self.globalRotDif.get_Daniso(), 'a.u.', 'Fixed'),
+                ('CSA', (np.mean(csa) if isinstance(csa, np.ndarray) else csa) * 1e6, 'ppm',
+                 'FixedMean' if isinstance(csa, np.ndarray) else 'Fixed'),
+                ('zeta', self.get_zeta(), 'a.u.', 'Fixed'))
+        for name, v, unit, tag in rows:
+            print('# %s %s: %g %s' % (tag, name, v, unit), file=fp)
+
+    def export_xvg(self, filePrefix, bIncludeExpt=False):
+        for i, sp in enumerate(self.spinrelax):
+            with open('%s%s.xvg' % (filePrefix, sp.get_suffix_from_conditions()), 'w') as fp:
+                sp.print_metadata('xmgrace', fp)
+                self.print_parameters('xmgrace', fp)
+                print('', file=fp)
+                print('@target s0', file=fp)
+                sp.print_values('xmgrace', fp)
+                if bIncludeExpt:
+                    print('@target s1', file=fp)
+                    d = self.data[i]
+                    print('@type xy' if d['dy'] is None else '@type xydy', file=fp)
+                    for k in range(len(d['y'])):
+                        print(("%s %g" % (d['names'][k], d['y'][k])) if d['dy'] is None
+                              else ("%s %g %g" % (d['names'][k], d['y'][k], d['dy'][k])), file=fp)
+                    print('&', file=fp)

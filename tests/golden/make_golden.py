@@ -272,6 +272,40 @@ def golden_relax():
          jomega_f32=npufunc.Jomega(x.astype(np.float32), y.astype(np.float32)), **res)
 
 
+def golden_relax_cli():
+    """calculate-relaxations-multi-field.py (prediction mode) run unmodified on a fittedCt file + histogram."""
+    import subprocess
+    import tempfile
+    fitCt = ref_loader.module("fitting_Ct_functions")
+    g = np.load(os.path.join(OUT, "relax.npz"))
+    with tempfile.TemporaryDirectory() as td:
+        e = np.empty(2, dtype=object); e[0] = g["edges_phi"]; e[1] = g["edges_cos"]
+        np.savez_compressed(td + "/h_vecHistogram.npz", names=np.arange(6), dataType="LambertCylindrical", bHistogram=True,
+                            edges=e, axisLabels=["phi", "cos(theta)"], data=g["hist"].astype(float))
+        ac = fitCt.autoCorrelations()
+        for i, row in enumerate(g["params"]):
+            nc = int(row[0])
+            m = ac.add_model(str(i), name=i, listC=list(row[2:2 + nc]), listTau=list(row[5:5 + nc]), S2=row[1])
+            m.bHasFit = True; m.chiSq = 0.1; m.dC = np.zeros(nc); m.dtau = np.zeros(nc); m.dS2 = 0.0
+        ac.import_target_array([str(i) for i in range(6)], [np.arange(1, 11.) * 10] * 6, [np.ones(10)] * 6)
+        ac.export(td + "/x_fittedCt.dat")
+        expt = {}
+        for t in ("R1", "R2", "NOE"):
+            expt[t] = "# Type %s\n# NucleiA 15N\n# NucleiB 1H\n# Frequency 600.133\n" % t + \
+                "".join("%d 1.0 0.1\n" % i for i in range(6))
+            with open(td + "/e_%s.dat" % t, "w") as fp:
+                fp.write(expt[t])
+        env = dict(os.environ, PYTHONPATH=os.pathsep.join([ref_loader.STUBS, ref_loader.REF_BUILD, ref_loader.REFERENCE]))
+        cmd = [sys.executable, ref_loader.REFERENCE + "/calculate-relaxations-multi-field.py", "-f", td + "/x_fittedCt.dat",
+               "--distfn", td + "/h_vecHistogram.npz", "-D", "2.1e-5", "--aniso", "1.35", "-o", td + "/ref",
+               td + "/e_R1.dat", td + "/e_R2.dat", td + "/e_NOE.dat"]
+        subprocess.run(cmd, env=env, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        out = {t: open(td + "/ref_15N1H_600MHz_%s.xvg" % t).read() for t in ("R1", "R2", "NOE")}
+        fitted = open(td + "/x_fittedCt.dat").read()
+    save("relax_cli.npz", fitted=np.array(fitted), **{"xvg_" + k: np.array(v) for k, v in out.items()},
+         **{"expt_" + k: np.array(v) for k, v in expt.items()})
+
+
 def main():
     if not ref_loader.available():
         sys.exit("reference tree not found at %s" % ref_loader.REFERENCE)
@@ -282,6 +316,7 @@ def main():
     golden_dq(refdq)
     golden_fit()
     golden_relax()
+    golden_relax_cli()
 
 
 if __name__ == "__main__":

@@ -125,3 +125,59 @@ def test_error_codes():
     import torch
     x = torch.zeros(16, device="cuda")
     assert lib.sr_ct_palmer_device(x.data_ptr(), 1, 100, 1, x.data_ptr(), x.data_ptr(), x.data_ptr(), 8, None) == -3
+
+
+def test_s2_and_average_vector(golden):
+    """Next-tier rows fused on the same stream: S2 by outer product (:96-145) and --vecAvg (:579-583)."""
+    from spinrelax_b200 import ct
+    g = golden("s2.npz")
+    v = g["vecs"]
+    s2 = ct.calculate_S2_by_outerProduct(v, 10.0, 10000.0)
+    assert s2.shape == g["s2_blocks"].shape
+    assert rel_err(s2[:, 0], g["s2_blocks"][:, 0]) < 1e-6
+    assert np.max(np.abs(s2[:, 1] - g["s2_blocks"][:, 1])) < 1e-6 * np.max(g["s2_blocks"][:, 0])
+    s2all = ct.calculate_S2_by_outerProduct(v)
+    assert rel_err(s2all, ct_oracle.s2_outer_product(v.astype(np.float64))) < 1e-6
+    q = np.array([0.83, -0.31, 0.22, 0.41])
+    avg = ct.average_vectors(v, q)
+    ref = ct_oracle.average_vector(ct_oracle.rotate_vectors(v, q))
+    assert np.max(np.abs(avg - ref)) < 1e-6
+
+
+def test_cli_ct_end_to_end(tmp_path, golden):
+    """The CLI mirror on .npy vector trajectories writes the reference's files; contents against the oracle."""
+    import contextlib, io
+    from spinrelax_b200 import cli_ct, io_formats, synth
+    v1 = synth.nh_vectors(2300, 5, seed=41)
+    v2 = synth.nh_vectors(1700, 5, seed=42)
+    np.save(tmp_path / "a.npy", v1)
+    np.save(tmp_path / "b.npy", v2)
+    pref = str(tmp_path / "rotdif")
+    with contextlib.redirect_stdout(io.StringIO()):
+        cli_ct.main(["-s", "ref.pdb", "-f", str(tmp_path / "a.npy"), str(tmp_path / "b.npy"), "--dt", "10", "--tau", "5000",
+                     "-o", pref, "--vecRot", "0.8 -0.36 0.48 0.0", "--vecHist", "--binary", "--vecAvg", "--S2", "--Ct"])
+    v4 = ct_oracle.reformat_by_tau([v1, v2], 10.0, 5000.0)
+    assert v4.shape == (7, 500, 5, 3)
+    legs, x, y, dy = io_formats.load_sxydylist(pref + "_Ctint.dat")
+    oCt, odCt = ct_oracle.ct_palmer(v4.astype(np.float64))
+    assert legs == ["1", "2", "3", "4", "5"] and np.array_equal(x[0], ct_oracle.ct_time_axis(10.0, 5000.0))
+    assert rel_err(y, oCt.T) < 2e-6 and np.max(np.abs(dy - odCt.T)) < 1e-6
+    q = np.array([0.8, -0.36, 0.48, 0.0])
+    z = np.load(pref + "_vecHistogram.npz", allow_pickle=True)
+    ho, eo = ct_oracle.sphere_histogram(v4.reshape(-1, 5, 3), q)
+    assert str(z["dataType"]) == "LambertCylindrical" and bool(z["bHistogram"])
+    assert np.array_equal(z["data"], ho) and np.array_equal(z["edges"][0], eo[0])
+    # the reference's reader accepts the file (spectral_densities.py:279-306 semantics)
+    from spinrelax_b200 import specdens
+    rot = specdens.globalRotationalDiffusion_Axisymmetric(D=[2e-5, 1.2])
+    rot.import_frame_vectors(pref + "_vecHistogram.npz")
+    assert rot.vecXH.shape == (2592, 5, 3) and rot.vecWeights.shape == (2592, 5)
+    s2 = np.loadtxt(pref + "_S2.dat", comments="&")
+    ref = ct_oracle.s2_outer_product(v4.reshape(-1, 5, 3).astype(np.float64), 10.0, 5000.0) * (1.02 / 1.04) ** 6
+    assert np.allclose(s2[:, 1:], ref, rtol=2e-5, atol=1e-7)
+    with pytest.raises(SystemExit) as e:
+        cli_ct.main(["-f", str(tmp_path / "a.npy"), "--Ct"])
+    assert e.value.code == 1
+    with pytest.raises(SystemExit) as e:
+        cli_ct.main(["-f", str(tmp_path / "a.npy"), "--vecRot", "1 1 0 0"])
+    assert e.value.code == 23

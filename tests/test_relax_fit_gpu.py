@@ -194,3 +194,36 @@ def test_fit_against_scipy_oracle_random():
     a, b = _rates(fitct, sd, ac), _rates(fitct, sd, ref)
     ok = [ac.model[str(i)].nParams == ref.model[str(i)].nParams for i in range(n)]
     assert rel_err(a[:, :, ok], b[:, :, ok]) < RTOL_RATE
+
+
+def test_cli_relax_and_fit_files(golden, tmp_path):
+    """CLI mirrors: calculate-relaxations-multi-field.py output text identical to the reference's; fittedCt
+    writer/reader round trip through calculate-fitted-Ct's mirror."""
+    import contextlib
+    from spinrelax_b200 import cli_fit, cli_relax, fitct, hist, io_formats
+    g, r = golden("relax_cli.npz"), golden("relax.npz")
+    (tmp_path / "x_fittedCt.dat").write_text(str(g["fitted"]))
+    hist.save_vec_histogram(str(tmp_path / "h_vecHistogram.npz"), np.arange(6), r["hist"].astype(np.float64),
+                            [r["edges_phi"], r["edges_cos"]])
+    files = []
+    for t in ("R1", "R2", "NOE"):
+        (tmp_path / ("e_%s.dat" % t)).write_text(str(g["expt_" + t]))
+        files.append(str(tmp_path / ("e_%s.dat" % t)))
+    with contextlib.redirect_stdout(io.StringIO()):
+        cli_relax.main(["-f", str(tmp_path / "x_fittedCt.dat"), "--distfn", str(tmp_path / "h_vecHistogram.npz"), "-D", "2.1e-5",
+                        "--aniso", "1.35", "-o", str(tmp_path / "ours")] + files)
+    for t in ("R1", "R2", "NOE"):
+        assert (tmp_path / ("ours_15N1H_600MHz_%s.xvg" % t)).read_text() == str(g["xvg_" + t]), t
+    # fit CLI: Ctint-format input -> fittedCt file that the reference-format reader parses back
+    f = golden("fit.npz")
+    t, Ct, dCt = f["t"], f["Ct"], f["dCt"]
+    io_formats.print_sxylist(str(tmp_path / "c_Ctint.dat"), list(range(1, 10)), t,
+                             np.stack((Ct.astype(np.float32), dCt.astype(np.float32)), axis=-1))
+    with contextlib.redirect_stdout(io.StringIO()):
+        cli_fit.main(["-f", str(tmp_path / "c_Ctint.dat"), "-o", str(tmp_path / "c")])
+    back = fitct.read_fittedCt_parameters(str(tmp_path / "c_fittedCt.dat"))
+    assert back.nModels == 9
+    for i, row in enumerate(f["ladder"]):
+        m = back.model[str(i + 1)]
+        if m.nParams == int(row[0]):
+            assert abs(m.S2 - row[2]) < 2e-4 * max(1.0, abs(row[2]))

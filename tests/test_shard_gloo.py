@@ -1,0 +1,72 @@
+"""N > 1 host logic on CPU: world_size-2 gloo process group exercising the vector / lag sharding helpers."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from spinrelax_b200 import shard
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, nR, nLags, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # vectors: each rank "computes" a (L, n_local) block whose entries encode (lag row, global vector id)
+        a, b = shard.split_range(nR, world, rank)
+        L = 7
+        local = torch.arange(L, dtype=torch.float32)[:, None] * 1000 + torch.arange(a, b, dtype=torch.float32)[None, :]
+        full = shard.gather_columns(local, nR, dst=0)
+        # lags: round-robin shard, rows encode the lag value
+        lags = np.arange(3, 3 + nLags)
+        mine = shard.shard_lags(lags, world, rank)
+        rows = torch.tensor(mine, dtype=torch.float64)[:, None].repeat(1, 6)
+        merged = shard.merge_lag_results(rows, lags, world, dst=0)
+        # frame-sharded histogram: all-reduce of integer counts
+        h = torch.full((3, 4), rank + 1, dtype=torch.int64)
+        shard.allreduce_sum_(h)
+        if rank == 0:
+            np.savez(os.path.join(out_dir, "r0.npz"), full=full.numpy(), merged=merged.numpy(), h=h.numpy())
+        else:
+            assert full is None and merged is None
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("nR,nLags", [(76, 100), (5, 3), (2, 1)])
+def test_gloo_world2(tmp_path, nR, nLags):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), nR, nLags, str(tmp_path)), nprocs=world, join=True)
+    r = np.load(tmp_path / "r0.npz")
+    L = 7
+    expect = np.arange(L)[:, None] * 1000 + np.arange(nR)[None, :]
+    assert np.array_equal(r["full"], expect.astype(np.float32))
+    assert np.array_equal(r["merged"][:, 0], np.arange(3, 3 + nLags))
+    assert (r["h"] == 3).all()
+
+
+def test_partition_properties():
+    for n in (1, 2, 76, 1000, 2001):
+        for world in (1, 2, 3, 4, 8):
+            blocks = [shard.split_range(n, world, r) for r in range(world)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == n
+            assert all(blocks[i][1] == blocks[i + 1][0] for i in range(world - 1))
+            sizes = shard.split_sizes(n, world)
+            assert sum(sizes) == n and max(sizes) - min(sizes) <= 1
+            lags = np.arange(n)
+            got = np.sort(np.concatenate([shard.shard_lags(lags, world, r) for r in range(world)]))
+            assert np.array_equal(got, lags)
+    v = np.zeros((2, 10, 7, 3))
+    assert shard.shard_vectors(v, 2, 0).shape == (2, 10, 4, 3) and shard.shard_vectors(v, 2, 1).shape == (2, 10, 3, 3)
