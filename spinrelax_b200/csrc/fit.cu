@@ -19,7 +19,7 @@ struct FitShared {
   double JtJ[kMaxP * kMaxP], Jtr[kMaxP], cost;
   double tJtJ[kMaxP * kMaxP], tJtr[kMaxP], tcost;
   double red[kFitThreads / 32][kNRed];
-  int flag;
+  int flag, trunc;
 };
 
 // accumulate cost, J^T r and J^T J of the model at parameters q over this thread's points, then block-reduce
@@ -161,26 +161,26 @@ ct_fit_lm_kernel(const double* __restrict__ T, const double* __restrict__ Y, con
       }
       double d[kMaxP];
       int ok = lm_step(sh.JtJ, sh.Jtr, fixed, nP, lam, d) ? 1 : 0;
-      // fraction-to-boundary rule: the trial point stays strictly inside the box (as SciPy's TRF iterates do),
-      // so a wild step can never park tau on 0 where the model has no gradient
-      double alpha = 1.0;
-      for (int i = 0; i < nP; ++i) {
-        if (d[i] < 0.0) alpha = fmin(alpha, 0.995 * (sh.p[i] - sh.lo[i]) / (-d[i]));
-        else if (d[i] > 0.0) alpha = fmin(alpha, 0.995 * (sh.hi[i] - sh.p[i]) / d[i]);
-      }
+      // per-coordinate fraction-to-boundary rule: a coordinate whose step would leave the box moves 99.5% of the
+      // way to that bound instead (the trial point stays strictly inside, as SciPy's TRF iterates do, so a wild
+      // step can never park tau on 0 where the model has no gradient); the other coordinates keep their step.
       double smax = 0.0;
+      int truncated = 0;
       for (int i = 0; i < nP; ++i) {
-        const double q = fmin(fmax(sh.p[i] + alpha * d[i], sh.lo[i]), sh.hi[i]);
+        double q = sh.p[i] + d[i];
+        if (q < sh.lo[i]) { q = sh.p[i] - 0.995 * (sh.p[i] - sh.lo[i]); truncated = 1; }
+        else if (q > sh.hi[i]) { q = sh.p[i] + 0.995 * (sh.hi[i] - sh.p[i]); truncated = 1; }
         smax = fmax(smax, fabs(q - sh.p[i]) / (fabs(sh.p[i]) + 1e-300));
         sh.ptry[i] = q;
       }
+      sh.trunc = truncated;
       sh.flag = ok ? (smax < 1e-15 ? 2 : 1) : 0;
     }
     __syncthreads();
-    const int flag = sh.flag;
+    const int flag = sh.flag, trunc = sh.trunc;
     __syncthreads();
     if (flag == 0) { lam *= 10.0; if (lam > 1e20) { status = 3; break; } continue; }
-    if (flag == 2) { status = 2; break; }      // step below machine precision
+    if (flag == 2 && !trunc) { status = 2; break; }      // step below machine precision
     evaluate<nP>(t, y, sig, L, sh.ptry, sh, sh.tJtJ, sh.tJtr, &sh.tcost);
     const double c0 = sh.cost, c1 = sh.tcost;
     const bool accept = (c1 <= c0) && (c1 == c1);
@@ -195,7 +195,7 @@ ct_fit_lm_kernel(const double* __restrict__ T, const double* __restrict__ Y, con
       __syncthreads();
       // converged: three consecutive negligible decreases taken with (almost) undamped Gauss-Newton steps.
       // A tiny decrease under heavy damping only means the step was short (flat multi-exponential valleys).
-      small = (c0 - c1 <= ftol * c0) ? small + 1 : 0;
+      small = (c0 - c1 <= ftol * c0 && !trunc) ? small + 1 : 0;    // a truncated step says nothing about convergence
       if (small >= 3 && lam <= 1e-7) { status = 1; ++it; break; }
     } else {
       lam *= 4.0;

@@ -193,7 +193,9 @@ def test_fit_against_scipy_oracle_random():
     assert agree >= n - 2
     a, b = _rates(fitct, sd, ac), _rates(fitct, sd, ref)
     ok = [ac.model[str(i)].nParams == ref.model[str(i)].nParams for i in range(n)]
-    assert rel_err(a[:, :, ok], b[:, :, ok]) < RTOL_RATE
+    assert rel_err(a[:, :2, ok], b[:, :2, ok]) < RTOL_RATE                       # R1, R2
+    # NOE crosses zero at 800 MHz for the poorly fitting 2-parameter models: 1e-4 of its O(1) scale
+    assert np.allclose(a[:, 2, ok], b[:, 2, ok], rtol=RTOL_RATE, atol=2e-5)
 
 
 def test_cli_relax_and_fit_files(golden, tmp_path):

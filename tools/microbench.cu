@@ -73,6 +73,82 @@ __global__ void __launch_bounds__(256) k_p2pattern(float* out, int iters, float 
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// ---- 2b. the K1 pattern WITH its shared-memory traffic: broadcast left vector + lane-strided window load
+// MODE 0: LDS.128 for both (the kernel as shipped in round 1)   1: no loads   2: window load only
+//      3: left-vector load only   4: SoA planes, 3 x LDS.32 each   5: left vector via SHFL from a per-lane
+//      register copy (one coalesced LDS.128 per 32 steps), window LDS.128   6: window via SHFL from the neighbour lane
+template <int R, int MODE>
+__global__ void __launch_bounds__(256, 2) k_p2pattern_lds(float* out, int iters) {
+  extern __shared__ float4 smv[];
+  float* smf = reinterpret_cast<float*>(smv);
+  const int n = 4096;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) smv[i] = make_float4(0.3f + 1e-4f * i, 0.4f - 1e-4f * i, 0.5f, 0.f);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int o = lane * R;
+  float wx[R], wy[R], wz[R], acc[R];
+#pragma unroll
+  for (int j = 0; j < R; ++j) { float4 v = smv[o + j]; wx[j] = v.x; wy[j] = v.y; wz[j] = v.z; acc[j] = 0.f; }
+  int s = warp * 64;
+  float4 areg = smv[lane];
+  float4 a = make_float4(0.3f, 0.4f, 0.5f, 0.f), nx = make_float4(0.31f, 0.41f, 0.51f, 0.f);
+  for (int it = 0; it < iters; ++it) {
+    if (MODE == 5 && (it & 1) == 0) areg = smv[(s + lane) & 2047];
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      if (MODE == 0 || MODE == 3) a = smv[(s + k) & 2047];
+      if (MODE == 0 || MODE == 2 || MODE == 5) nx = smv[((s + k) & 1023) + o + R];
+      if (MODE == 4) {
+        const int ia = (s + k) & 2047, iw = ((s + k) & 1023) + o + R;
+        a.x = smf[ia]; a.y = smf[4096 + ia]; a.z = smf[8192 + ia];
+        nx.x = smf[iw]; nx.y = smf[4096 + iw]; nx.z = smf[8192 + iw];
+      }
+      if (MODE == 7) {   // left vector SoA scalar broadcast, window LDS.128
+        const int ia = (s + k) & 2047;
+        a.x = smf[ia]; a.y = smf[4096 + ia]; a.z = smf[8192 + ia];
+        nx = smv[((s + k) & 1023) + o + R];
+      }
+      if (MODE == 8) {   // left vector LDS.128, window SoA scalars
+        const int iw = ((s + k) & 1023) + o + R;
+        a = smv[(s + k) & 2047];
+        nx.x = smf[iw]; nx.y = smf[4096 + iw]; nx.z = smf[8192 + iw];
+      }
+      if (MODE == 9) {   // AoS float4 in memory, but read as LDS.64 (xy) + LDS.32 (z): no fourth register written
+        const int ia = (s + k) & 2047, iw = ((s + k) & 1023) + o + R;
+        const float2 axy = *reinterpret_cast<const float2*>(&smv[ia]); a.x = axy.x; a.y = axy.y; a.z = smf[4 * ia + 2];
+        const float2 wxy = *reinterpret_cast<const float2*>(&smv[iw]); nx.x = wxy.x; nx.y = wxy.y; nx.z = smf[4 * iw + 2];
+      }
+      if (MODE == 5) {
+        const int src = (k + (it & 1) * R) & 31;
+        a.x = __shfl_sync(0xffffffffu, areg.x, src); a.y = __shfl_sync(0xffffffffu, areg.y, src);
+        a.z = __shfl_sync(0xffffffffu, areg.z, src);
+      }
+      if (MODE == 6) {
+        a = smv[(s + k) & 2047];
+        nx.x = __shfl_down_sync(0xffffffffu, wx[k], 1); nx.y = __shfl_down_sync(0xffffffffu, wy[k], 1);
+        nx.z = __shfl_down_sync(0xffffffffu, wz[k], 1);
+        if (lane == 31) { const float4 t4 = smv[((s + k) & 1023) + o + R]; nx.x = t4.x; nx.y = t4.y; nx.z = t4.z; }
+      }
+      if (MODE == 1 || MODE == 3) { nx.x += 1e-7f; }
+      if (MODE == 1 || MODE == 2) { a.x += 1e-8f; }
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        const int sl = (k + j) % R;
+        float d = a.x * wx[sl];
+        d = fmaf(a.y, wy[sl], d);
+        d = fmaf(a.z, wz[sl], d);
+        acc[j] = fmaf(d, d, acc[j]);
+      }
+      wx[k] = nx.x; wy[k] = nx.y; wz[k] = nx.z;
+    }
+    s += R;
+  }
+  float t = 0.f;
+#pragma unroll
+  for (int j = 0; j < R; ++j) t += acc[j];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = t;
+}
+
 // ---- 3. packed FFMA2 (fma.rn.f32x2), 16 independent 64-bit chains ------------------------------
 __device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
   uint64_t d;
@@ -304,6 +380,19 @@ int main() {
     ms = time_ms([&] { k_p2pattern<16><<<grid, block>>>(d, iters, 0.7f); });
     pairs = nthr * iters * 16 * 16;
     printf("{\"probe\":\"p2pattern_R16\",\"ms\":%.3f,\"pairs_per_s\":%.4g,\"tflops7\":%.2f}\n", ms, pairs / ms * 1e3, pairs * 7 / ms * 1e-9);
+    {
+      size_t smem = 4096 * 16 + 1024;
+      const int g2 = g_sms * 2;
+      const double nthr2 = (double)g2 * block;
+      int it2 = 6000;
+#define LDS_PROBE(MODE)                                                                                         \
+      CK(cudaFuncSetAttribute(k_p2pattern_lds<15, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      ms = time_ms([&] { k_p2pattern_lds<15, MODE><<<g2, block, smem>>>(d, it2); });                              \
+      pairs = nthr2 * it2 * 15 * 15;                                                                              \
+      printf("{\"probe\":\"p2pattern_lds_R15_mode%d\",\"ms\":%.3f,\"pairs_per_s\":%.4g,\"tflops7\":%.2f}\n", MODE, ms, pairs / ms * 1e3, pairs * 7 / ms * 1e-9);
+      LDS_PROBE(0) LDS_PROBE(3) LDS_PROBE(4) LDS_PROBE(5) LDS_PROBE(7) LDS_PROBE(8) LDS_PROBE(9)
+#undef LDS_PROBE
+    }
   }
   {
     int iters = 3000;
