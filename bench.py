@@ -40,7 +40,7 @@ def workload_config(n_gpus):
                                                                              N_FRAMES_PER_CHUNK // 2),
             "n_vectors_per_gpu": N_VEC, "n_chunks": N_CHUNK, "frames_per_chunk": N_FRAMES_PER_CHUNK,
             "max_lag": N_FRAMES_PER_CHUNK // 2, "sharding": "bond vectors, %d per rank" % N_VEC,
-            "l2": "inputs (0.9 GB AoS, 1.2 GB packed) exceed the 126 MB L2; no flush needed",
+            "l2": "inputs (0.9 GB AoS, 0.9 GB packed SoA) exceed the 126 MB L2; no flush needed",
             "pairs_per_step_per_gpu": n_pairs(N_VEC, N_CHUNK, N_FRAMES_PER_CHUNK, N_FRAMES_PER_CHUNK // 2)}
 
 

@@ -45,13 +45,14 @@ int sr_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* global_m
  * delta = 1 (lag 0 is never computed, :222).
  * ---------------------------------------------------------------------------------------------- */
 
-/* frames of zero padding appended to every (vector, chunk) row of the packed stream */
+/* row pitch (frames, multiple of 4) of the packed stream: nF plus the zero padding K1's tiles read past the end */
 long long sr_ct_row_pitch(long long nF);
 
-/* bytes of device scratch needed by sr_ct_palmer_device: packed float4 stream + FP64 lag sums */
+/* bytes of device scratch needed by sr_ct_palmer_device: packed SoA stream (12 B per frame) + FP64 lag sums */
 size_t sr_ct_workspace_bytes(int nC, long long nF, int nR);
 
-/* K2: (nC, nF, nR, 3) float32 AoS -> vector-major float4 stream U[nR][nC][pitch] (x,y,z,0), rows
+/* K2: (nC, nF, nR, 3) float32 AoS -> vector-major structure-of-arrays stream U[nR][nC][3][pitch] float32
+ * (one X, Y and Z plane per (vector, chunk) row; 16-byte aligned, nR*nC*3*pitch*4 bytes), planes
  * zero-padded to `pitch` frames.  If q_rot != NULL (host pointer to 4 doubles, w x y z) the vectors
  * are rotated by the normalised quaternion first (rotate_vector_simd, transforms3d_supplement.py:270-296). */
 int sr_pack_vectors_f32(const float* d_vecs, int nC, long long nF, int nR, const double* h_q_rot,

@@ -62,6 +62,9 @@ __device__ __forceinline__ void sr_mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
   } while (!ok);
 }
+__device__ __forceinline__ void sr_mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sr_smem_u32(bar)) : "memory");
+}
 // generic-proxy reads of a stage are done; order them before the next async-proxy write into it
 __device__ __forceinline__ void sr_fence_proxy_async() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

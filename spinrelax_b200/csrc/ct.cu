@@ -5,18 +5,26 @@
 namespace {
 
 // ------------------------------------------------------------------------------------------------
-// K1 geometry.  One CTA = one (vector, chunk, lag tile).  Inside the CTA every lane owns R consecutive
-// lags (lane l: d0 + l*R + j), so a warp covers TL = 32*R lags and the left vector u(t) is a
-// shared-memory broadcast.  R is odd so that the strided LDS.128 of the sliding window
-// (lane stride = R float4) is bank-conflict free.  The 8 warps split each staged frame tile of
-// TF = 8 * R * MB frames; each lane keeps its R window vectors in registers and slides them by one
+// Packed stream layout (K2 -> K1): one row per (vector, chunk) made of three float32 planes
+//   row = [ X[pitch] | Y[pitch] | Z[pitch] ],  frames >= nF are zero,  pitch % 4 == 0  (16-byte planes for TMA)
+// i.e. 12 algorithmic bytes per frame, structure-of-arrays.  SoA matters for K1: the left vector u(t) is read
+// with three broadcast LDS.32 and the window frame with three lane-strided LDS.32, which costs measurably
+// fewer issue cycles than two LDS.128 of (x,y,z,0) records (tools/microbench.cu, modes 0 vs 4: +8 %).
+//
+// K1 geometry.  One CTA = one (vector, chunk, lag tile).  Tile lt covers the lags lt*TL .. lt*TL + TL - 1
+// (lag 0 of tile 0 is computed and dropped: starting tiles at multiples of TL keeps every TMA source
+// 16-byte aligned).  Inside the CTA every lane owns R consecutive lags (lane l: D0 + l*R + j), so a warp
+// covers TL = 32*R lags and the left vector u(t) is a shared-memory broadcast.  R is odd so that the
+// lane-strided window loads (stride R floats) are bank-conflict free.  The NW warps split each staged frame
+// tile of TF = NW * R * MB frames; each lane keeps its R window vectors in registers and slides them by one
 // frame per step (static circular indexing, fully unrolled over R), so one step costs
-// 2 LDS.128 + 4R FMA-pipe instructions.
+// 6 LDS.32 + 4R FMA-pipe instructions.
 // ------------------------------------------------------------------------------------------------
-// Tile geometry is a compile-time configuration; kDefaultVariant is what the product launches, the other
-// instantiations exist so that tools/tune_ct.py can time them on the GPU.
-template <int R_, int MB_, int FB_, int NW_, int MINB_>
+// Tile geometry is a compile-time configuration; kLongVariant / kShortVariant are what the product launches,
+// the other instantiations exist so that tools/tune_ct.py can time them on the GPU.
+template <int R_, int MB_, int FB_, int NW_, int MINB_, int NS_ = 2>
 struct CtCfg {
+  static constexpr int NS = NS_;          // TMA stages in the ring
   static constexpr int R = R_;            // lags per lane (odd)
   static constexpr int MB = MB_;          // R-step blocks per warp per frame tile
   static constexpr int FB = FB_;          // blocks between FP32 -> FP64 flushes (R*FB terms per FP32 partial sum)
@@ -25,68 +33,93 @@ struct CtCfg {
   static constexpr int TFW = R * MB;      // frames per warp per tile
   static constexpr int TF = NW * TFW;     // frames per tile
   static constexpr int TL = 32 * R;       // lags per tile
-  static constexpr int StageVecs = TF + (TF + TL);   // left range + window range, float4 each
-  static constexpr int StageBytes = StageVecs * 16;
-  static constexpr int SmemBytes = 2 * StageBytes;
-  static_assert(R % 2 == 1, "R must be odd: lane stride of the window LDS.128 has to be conflict free");
+  static constexpr int TW = TF + TL;      // window frames per tile
+  static constexpr int StageFloats = 3 * TF + 3 * TW;   // LX LY LZ WX WY WZ
+  static constexpr int StageBytes = StageFloats * 4;
+  static constexpr int SmemBytes = NS * StageBytes;
+  static_assert(R % 2 == 1, "R must be odd: lane stride of the window loads has to be conflict free");
   static_assert(MB % FB == 0, "flush interval must divide the warp tile");
+  static_assert(TF % 4 == 0 && TL % 4 == 0, "TMA sources and destinations must stay 16-byte aligned");
   static_assert(NW * TL * 8 <= SmemBytes, "epilogue reduction buffer must fit in the stage buffers");
 };
 
 template <class Cfg>
 __global__ void __launch_bounds__(Cfg::NW * 32, Cfg::MINB)
-ct_lag_kernel(const float4* __restrict__ U, long long pitch, int nF, int L, int nLT, double* __restrict__ S) {
+ct_lag_kernel(const float* __restrict__ U, long long pitch, int nF, int L, int nLT, double* __restrict__ S) {
   constexpr int kR = Cfg::R, kMB = Cfg::MB, kFB = Cfg::FB, kNW = Cfg::NW, kTFW = Cfg::TFW, kTF = Cfg::TF,
-                kTL = Cfg::TL, kStageVecs = Cfg::StageVecs, kStageBytes = Cfg::StageBytes;
+                kTL = Cfg::TL, kTW = Cfg::TW, kStageFloats = Cfg::StageFloats, kStageBytes = Cfg::StageBytes;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ __align__(8) uint64_t full_bar[2];
-  float4* const stage_base = reinterpret_cast<float4*>(smem_raw);
+  __shared__ __align__(8) uint64_t full_bar[Cfg::NS], empty_bar[Cfg::NS];
+  constexpr int kNS = Cfg::NS;
+  float* const stage_base = reinterpret_cast<float*>(smem_raw);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long item = blockIdx.x;
   const long long rc = item / nLT;
   const int lt = (int)(item % nLT);
-  const int d0 = 1 + lt * kTL;      // smallest lag of this tile
+  const int d0 = lt * kTL;          // smallest lag of this tile
   const int nSteps = nF - d0;       // t in [0, nSteps) has at least one valid pair in this tile
   const int nTiles = (nSteps + kTF - 1) / kTF;
-  const float4* const row = U + rc * pitch;
+  const float* const rowX = U + rc * 3 * pitch;
+  const float* const rowY = rowX + pitch;
+  const float* const rowZ = rowY + pitch;
 
   if (tid == 0) {
-    sr_mbar_init(&full_bar[0], 1);
-    sr_mbar_init(&full_bar[1], 1);
+#pragma unroll
+    for (int i = 0; i < kNS; ++i) { sr_mbar_init(&full_bar[i], 1); sr_mbar_init(&empty_bar[i], kNW); }
     sr_fence_barrier_init();
   }
   __syncthreads();
 
-  auto issue = [&](int k) {
-    const int st = k & 1;
-    float4* Ls = stage_base + st * kStageVecs;
-    float4* Ws = Ls + kTF;
+  auto issue = [&](int k, int st) {
+    float* sb = stage_base + st * kStageFloats;
+    const long long f = (long long)k * kTF;
     sr_mbar_expect_tx(&full_bar[st], kStageBytes);
-    sr_tma_load_1d(Ls, row + (long long)k * kTF, kTF * 16, &full_bar[st]);
-    sr_tma_load_1d(Ws, row + (long long)k * kTF + d0, (kTF + kTL) * 16, &full_bar[st]);
+    sr_tma_load_1d(sb, rowX + f, kTF * 4, &full_bar[st]);
+    sr_tma_load_1d(sb + kTF, rowY + f, kTF * 4, &full_bar[st]);
+    sr_tma_load_1d(sb + 2 * kTF, rowZ + f, kTF * 4, &full_bar[st]);
+    sr_tma_load_1d(sb + 3 * kTF, rowX + f + d0, kTW * 4, &full_bar[st]);
+    sr_tma_load_1d(sb + 3 * kTF + kTW, rowY + f + d0, kTW * 4, &full_bar[st]);
+    sr_tma_load_1d(sb + 3 * kTF + 2 * kTW, rowZ + f + d0, kTW * 4, &full_bar[st]);
   };
 
   double acc64[kR];
 #pragma unroll
   for (int j = 0; j < kR; ++j) acc64[j] = 0.0;
 
-  if (tid == 0 && nTiles > 0) issue(0);
+  // Ring of kNS stages.  Thread 0 is the producer: before tile k it refills the stage that tile k-1 used
+  // (tile k + kNS - 1), waiting on that stage's "empty" barrier (one arrival per warp).  Consumer warps
+  // never meet at a CTA-wide barrier inside the loop, so a warp that finishes its share of a tile early
+  // starts the next one at once.
+  if (tid == 0)
+    for (int i = 0; i < kNS - 1 && i < nTiles; ++i) issue(i, i);
   const int o = lane * kR;   // lag offset of this lane inside the tile
   const int s0 = warp * kTFW;
 
+  int st = 0, ph = 0;                 // stage and full-barrier parity of tile k
+  int pst = kNS - 1, pph = 1;         // producer: stage of tile k + kNS - 1; parity of the empty barrier ((kn / kNS) - 1) & 1
   for (int k = 0; k < nTiles; ++k) {
-    if (tid == 0 && k + 1 < nTiles) issue(k + 1);   // stage (k+1)&1 was released by the barrier ending tile k-1
-    sr_mbar_wait(&full_bar[k & 1], (k >> 1) & 1);
-    const float4* __restrict__ Ls = stage_base + (k & 1) * kStageVecs;
-    const float4* __restrict__ Ws = Ls + kTF;
+    if (tid == 0) {
+      const int kn = k + kNS - 1;
+      if (kn < nTiles) {
+        if (kn >= kNS) { sr_mbar_wait(&empty_bar[pst], pph); sr_fence_proxy_async(); }
+        issue(kn, pst);
+      }
+    }
+    if (++pst == kNS) { pst = 0; pph ^= 1; }
+    sr_mbar_wait(&full_bar[st], ph);
+    const float* __restrict__ LX = stage_base + st * kStageFloats;
+    const float* __restrict__ LY = LX + kTF;
+    const float* __restrict__ LZ = LY + kTF;
+    const float* __restrict__ WX = LZ + kTF;
+    const float* __restrict__ WY = WX + kTW;
+    const float* __restrict__ WZ = WY + kTW;
 
     if (k * kTF + s0 < nSteps) {   // warp-uniform: whole warp range is past the last valid pair otherwise
       float wx[kR], wy[kR], wz[kR];
 #pragma unroll
       for (int j = 0; j < kR; ++j) {
-        const float4 v = Ws[s0 + o + j];
-        wx[j] = v.x; wy[j] = v.y; wz[j] = v.z;
+        wx[j] = WX[s0 + o + j]; wy[j] = WY[s0 + o + j]; wz[j] = WZ[s0 + o + j];
       }
 #pragma unroll 1
       for (int b = 0; b < kMB; b += kFB) {
@@ -98,26 +131,29 @@ ct_lag_kernel(const float4* __restrict__ U, long long pitch, int nF, int L, int 
           const int s = s0 + (b + bb) * kR;
 #pragma unroll
           for (int kk = 0; kk < kR; ++kk) {
-            const float4 a = Ls[s + kk];                 // u(t), broadcast
-            const float4 nx = Ws[s + kk + o + kR];       // frame entering the window
+            const float ax = LX[s + kk], ay = LY[s + kk], az = LZ[s + kk];   // u(t), broadcast
+            const int iw = s + kk + o + kR;                                  // frame entering the window
+            const float nx = WX[iw], ny = WY[iw], nz = WZ[iw];
 #pragma unroll
             for (int j = 0; j < kR; ++j) {
               const int sl = (kk + j) % kR;              // slot holding frame t + d0 + o + j
-              float d = a.x * wx[sl];
-              d = fmaf(a.y, wy[sl], d);
-              d = fmaf(a.z, wz[sl], d);
+              float d = ax * wx[sl];
+              d = fmaf(ay, wy[sl], d);
+              d = fmaf(az, wz[sl], d);
               acc[j] = fmaf(d, d, acc[j]);
             }
-            wx[kk] = nx.x; wy[kk] = nx.y; wz[kk] = nx.z;
+            wx[kk] = nx; wy[kk] = ny; wz[kk] = nz;
           }
         }
 #pragma unroll
         for (int j = 0; j < kR; ++j) acc64[j] += (double)acc[j];
       }
     }
-    sr_fence_proxy_async();
-    __syncthreads();
+    __syncwarp();
+    if (lane == 0) sr_mbar_arrive(&empty_bar[st]);
+    if (++st == kNS) { st = 0; ph ^= 1; }
   }
+  __syncthreads();
 
   // cross-warp reduction through the (now idle) stage buffers, one store per lag
   double* red = reinterpret_cast<double*>(smem_raw);
@@ -129,56 +165,80 @@ ct_lag_kernel(const float4* __restrict__ U, long long pitch, int nF, int L, int 
 #pragma unroll
     for (int w = 0; w < kNW; ++w) s += red[w * kTL + i];
     const int lag = d0 + i;
-    if (lag <= L) S[rc * (long long)L + (lag - 1)] = s;
+    if (lag >= 1 && lag <= L) S[rc * (long long)L + (lag - 1)] = s;
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// K2: AoS (chunk, frame, vector, xyz) float32 -> vector-major float4 rows with zero padding.
-// Tile = 64 frames x 32 vectors through shared memory so that both sides are coalesced.
+// K2: AoS (chunk, frame, vector, xyz) float32 -> vector-major SoA rows (three planes) with zero padding.
+// CTA = (chunk, tile of 64 frames, group of 16 vectors).  The 64 x 48-float tile is read with LDG.128 (a
+// frame row of the reference layout is a multiple of 16 bytes when nR % 4 == 0; scalar loads otherwise),
+// staged in shared memory with a 50-float row pitch, and written out as 48 plane rows of 64 floats with
+// STG.128.  A warp stores 8 plane rows x 64 contiguous bytes, which makes the transposed shared-memory reads
+// bank-conflict free ((200 q + p) mod 32 is a bijection for q < 4, p < 8).  HBM-bound: 12 B in + 12 B out.
 // ------------------------------------------------------------------------------------------------
-constexpr int kPF = 64, kPV = 32;
+constexpr int kPF = 64, kPV = 16, kPP = 50, kPT = 256;
 
-__global__ void __launch_bounds__(256)
-pack_kernel(const float* __restrict__ vecs, int nC, long long nF, int nR, float4* __restrict__ U, long long pitch,
+template <bool VEC4>
+__global__ void __launch_bounds__(kPT)
+pack_kernel(const float* __restrict__ vecs, int nC, long long nF, int nR, float* __restrict__ U, long long pitch,
             int do_rot, double qw, double qx, double qy, double qz) {
-  __shared__ float tile[kPF][kPV * 3 + 1];
+  __shared__ float tile[kPF * kPP];
   const int c = blockIdx.z;
   const long long f0 = (long long)blockIdx.x * kPF;
   const int r0 = blockIdx.y * kPV;
   const int nv = min(kPV, nR - r0);
   const int tid = threadIdx.x;
 
-  if (f0 < nF) {
-    const int rowlen = nv * 3;
-    for (int e = tid; e < kPF * rowlen; e += 256) {
-      const int fl = e / rowlen, col = e - fl * rowlen;
+  // ---- load: 64 frames x (3 nv) floats, zero beyond nF (the padding region of the packed rows) ----
+  if (VEC4) {
+    const int n4 = (3 * nv) >> 2;                       // float4 per frame row of this group (nv % 4 == 0)
+    for (int idx = tid; idx < kPF * 12; idx += kPT) {
+      const int fl = idx / 12, k4 = idx - fl * 12;
+      const long long f = f0 + fl;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (f < nF && k4 < n4)
+        v = __ldg(reinterpret_cast<const float4*>(vecs + (((long long)c * nF + f) * nR + r0) * 3) + k4);
+      float* t = tile + fl * kPP + 4 * k4;
+      t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w;
+    }
+  } else {
+    for (int idx = tid; idx < kPF * 48; idx += kPT) {
+      const int fl = idx / 48, k = idx - fl * 48;
       const long long f = f0 + fl;
       float v = 0.f;
-      if (f < nF) v = vecs[(((long long)c * nF + f) * nR + r0) * 3 + col];
-      tile[fl][col] = v;
+      if (f < nF && k < 3 * nv) v = __ldg(vecs + (((long long)c * nF + f) * nR + r0) * 3 + k);
+      tile[fl * kPP + k] = v;
     }
   }
   __syncthreads();
-  for (int e = tid; e < kPF * nv; e += 256) {
-    const int rl = e / kPF, fl = e - rl * kPF;
-    const long long f = f0 + fl;
-    if (f >= pitch) continue;
-    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (f < nF) {
-      float x = tile[fl][rl * 3 + 0], y = tile[fl][rl * 3 + 1], z = tile[fl][rl * 3 + 2];
-      if (do_rot) {
-        // a = q_v x v + q_w v ; b = q_v x a ; out = b + b + v   (transforms3d_supplement.py:283-296)
-        const double vx = x, vy = y, vz = z;
-        const double ax = qy * vz - qz * vy + qw * vx;
-        const double ay = qz * vx - qx * vz + qw * vy;
-        const double az = qx * vy - qy * vx + qw * vz;
-        const double bx = qy * az - qz * ay, by = qz * ax - qx * az, bz = qx * ay - qy * ax;
-        x = (float)(bx + bx + vx); y = (float)(by + by + vy); z = (float)(bz + bz + vz);
-      }
-      o = make_float4(x, y, z, 0.f);
+  if (do_rot) {
+    // a = q_v x v + q_w v ; b = q_v x a ; out = b + b + v   (transforms3d_supplement.py:283-296), float64 like the reference
+    for (int idx = tid; idx < kPF * kPV; idx += kPT) {
+      const int fl = idx >> 4, v = idx & 15;
+      float* t = tile + fl * kPP + 3 * v;
+      const double vx = t[0], vy = t[1], vz = t[2];
+      const double ax = qy * vz - qz * vy + qw * vx;
+      const double ay = qz * vx - qx * vz + qw * vy;
+      const double az = qx * vy - qy * vx + qw * vz;
+      const double bx = qy * az - qz * ay, by = qz * ax - qx * az, bz = qx * ay - qy * ax;
+      t[0] = (float)(bx + bx + vx); t[1] = (float)(by + by + vy); t[2] = (float)(bz + bz + vz);
     }
-    U[((long long)(r0 + rl) * nC + c) * pitch + f] = o;
+    __syncthreads();
+  }
+  // ---- store: plane row k = 3 v + comp, 16 float4 per row ----
+  const int lane = tid & 31, warp = tid >> 5;
+  const int prl = lane >> 2, q = lane & 3;
+  for (int w = warp; w < 24; w += kPT / 32) {
+    const int k = (w % 6) * 8 + prl;                    // tile column
+    const int fq = (w / 6) * 4 + q;                     // float4 index inside the 64-frame row
+    const int v = k / 3, comp = k - 3 * v;
+    const long long f = f0 + 4 * fq;
+    if (v < nv && f < pitch) {
+      const float* t = tile + (4 * fq) * kPP + k;
+      const float4 o = make_float4(t[0], t[kPP], t[2 * kPP], t[3 * kPP]);
+      *reinterpret_cast<float4*>(U + (((long long)(r0 + v) * nC + c) * 3 + comp) * pitch + f) = o;
+    }
   }
 }
 
@@ -212,22 +272,31 @@ ct_finalize_kernel(const double* __restrict__ S, int nC, int nF, int nR, int L, 
 // ================================================================================================
 // C ABI
 // ================================================================================================
-// variants (R, MB, FB, NW, CTAs/SM); tools/tune_ct.py times them, kDefaultVariant is the product path
-using CtV0 = CtCfg<15, 8, 1, 8, 2>;
-using CtV1 = CtCfg<15, 8, 2, 8, 2>;
-using CtV2 = CtCfg<15, 8, 4, 8, 2>;
-using CtV3 = CtCfg<15, 8, 2, 8, 1>;
-using CtV4 = CtCfg<15, 8, 2, 12, 1>;
-using CtV5 = CtCfg<13, 8, 2, 8, 2>;
-using CtV6 = CtCfg<17, 8, 2, 8, 2>;
-using CtV7 = CtCfg<15, 12, 2, 8, 2>;
-constexpr int kNumVariants = 8;
-constexpr int kDefaultVariant = 0;   // flush every 15 terms: dCt stays within 1e-5 of the float64 reference
-constexpr int kMaxTF = 1440, kMaxTL = 32 * 17;   // padding must cover the largest tile of any variant
+// variants (R, MB, FB, NW, CTAs/SM, stages); tools/tune_ct.py times them.  The product path launches
+// kLongVariant for long chunks and kShortVariant (smaller lag / frame tiles) for short ones.
+using CtV0 = CtCfg<15, 8, 1, 8, 2, 2>;
+using CtV1 = CtCfg<15, 8, 2, 8, 2, 2>;
+using CtV2 = CtCfg<15, 8, 4, 8, 2, 2>;
+using CtV3 = CtCfg<19, 6, 2, 12, 1, 2>;
+using CtV4 = CtCfg<19, 6, 2, 12, 1, 3>;
+using CtV5 = CtCfg<15, 8, 2, 8, 2, 3>;
+using CtV6 = CtCfg<17, 8, 2, 8, 2, 3>;
+using CtV7 = CtCfg<15, 12, 2, 8, 2, 3>;
+using CtV8 = CtCfg<21, 4, 2, 12, 1, 3>;
+using CtV9 = CtCfg<19, 4, 2, 12, 1, 4>;
+using CtV10 = CtCfg<19, 6, 1, 12, 1, 3>;
+using CtV11 = CtCfg<17, 6, 2, 12, 1, 3>;
+using CtV12 = CtCfg<15, 8, 1, 8, 2, 3>;
+constexpr int kNumVariants = 13;
+constexpr int kLongVariant = 4;      // R = 19, 12 warps, 1 CTA/SM, 3 stages: 38 terms per FP32 partial sum
+constexpr int kShortVariant = 12;    // R = 15, 8 warps, 2 CTAs/SM, 3 stages: 15 terms per FP32 partial sum (few chunk
+                                     // means enter dCt when chunks are short, so keep its rounding at the 1e-7 level)
+constexpr long long kShortFrames = 8192;
+constexpr int kMaxTF = 1440, kMaxTL = 32 * 21;   // padding must cover the largest tile of any variant
 
 template <class Cfg>
-int launch_ct_lag(const float4* U, long long pitch, long long nF, int nRC, long long L, double* S, cudaStream_t st) {
-  const long long nLT = (L + Cfg::TL - 1) / Cfg::TL;
+int launch_ct_lag(const float* U, long long pitch, long long nF, int nRC, long long L, double* S, cudaStream_t st) {
+  const long long nLT = (L + Cfg::TL) / Cfg::TL;   // tiles start at lag 0: ceil((L + 1) / TL)
   const long long items = (long long)nRC * nLT;
   SR_REQUIRE(items < (1LL << 31), "sr_ct_lag_sums: %lld work items exceed the grid limit", items);
   SR_CUDA(cudaFuncSetAttribute(ct_lag_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SmemBytes));
@@ -243,7 +312,7 @@ extern "C" long long sr_ct_row_pitch(long long nF) { return sr_round_up(nF + kMa
 extern "C" size_t sr_ct_workspace_bytes(int nC, long long nF, int nR) {
   const long long pitch = sr_ct_row_pitch(nF);
   const long long L = nF / 2;
-  size_t packed = (size_t)nR * nC * pitch * 16;
+  size_t packed = (size_t)nR * nC * pitch * 12;
   size_t sums = (size_t)nR * nC * L * 8;
   return sr_round_up((long long)packed, 256) + sr_round_up((long long)sums, 256);
 }
@@ -252,7 +321,8 @@ extern "C" int sr_pack_vectors_f32(const float* d_vecs, int nC, long long nF, in
                                    void* d_packed, long long pitch, void* stream) {
   SR_REQUIRE(d_vecs && d_packed, "sr_pack_vectors_f32: null pointer");
   SR_REQUIRE(nC > 0 && nF > 0 && nR > 0, "sr_pack_vectors_f32: empty shape (nC=%d nF=%lld nR=%d)", nC, nF, nR);
-  SR_REQUIRE(pitch >= nF, "sr_pack_vectors_f32: pitch %lld < nF %lld", pitch, nF);
+  SR_REQUIRE(pitch >= nF && pitch % 4 == 0, "sr_pack_vectors_f32: pitch %lld must be >= nF %lld and a multiple of 4", pitch, nF);
+  SR_REQUIRE(((uintptr_t)d_packed & 15) == 0, "sr_pack_vectors_f32: packed stream must be 16-byte aligned");
   SR_REQUIRE(nC <= 65535, "sr_pack_vectors_f32: nC %d exceeds grid limit", nC);
   double q[4] = {1, 0, 0, 0};
   int do_rot = 0;
@@ -264,8 +334,12 @@ extern "C" int sr_pack_vectors_f32(const float* d_vecs, int nC, long long nF, in
     do_rot = 1;
   }
   dim3 grid((unsigned)((pitch + kPF - 1) / kPF), (unsigned)((nR + kPV - 1) / kPV), (unsigned)nC);
-  pack_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_vecs, nC, nF, nR, (float4*)d_packed, pitch, do_rot, q[0], q[1],
-                                                      q[2], q[3]);
+  if (nR % 4 == 0 && ((uintptr_t)d_vecs & 15) == 0)
+    pack_kernel<true><<<grid, kPT, 0, (cudaStream_t)stream>>>(d_vecs, nC, nF, nR, (float*)d_packed, pitch, do_rot, q[0],
+                                                              q[1], q[2], q[3]);
+  else
+    pack_kernel<false><<<grid, kPT, 0, (cudaStream_t)stream>>>(d_vecs, nC, nF, nR, (float*)d_packed, pitch, do_rot, q[0],
+                                                               q[1], q[2], q[3]);
   SR_CUDA(cudaGetLastError());
   return SR_OK;
 }
@@ -279,7 +353,8 @@ extern "C" int sr_ct_lag_sums_variant(const void* d_packed, long long pitch, int
   SR_REQUIRE(pitch >= nF + kMaxTF + kMaxTL, "sr_ct_lag_sums: pitch %lld lacks %d frames of zero padding", pitch,
              kMaxTF + kMaxTL);
   SR_REQUIRE((long long)nR * nC < (1LL << 31), "sr_ct_lag_sums: too many (vector, chunk) rows");
-  const float4* U = (const float4*)d_packed;
+  SR_REQUIRE(pitch % 4 == 0 && ((uintptr_t)d_packed & 15) == 0, "sr_ct_lag_sums: packed stream must be 16-byte aligned with pitch %% 4 == 0");
+  const float* U = (const float*)d_packed;
   cudaStream_t st = (cudaStream_t)stream;
   const int nRC = nR * nC;
   switch (variant) {
@@ -291,6 +366,11 @@ extern "C" int sr_ct_lag_sums_variant(const void* d_packed, long long pitch, int
     case 5: return launch_ct_lag<CtV5>(U, pitch, nF, nRC, L, d_S, st);
     case 6: return launch_ct_lag<CtV6>(U, pitch, nF, nRC, L, d_S, st);
     case 7: return launch_ct_lag<CtV7>(U, pitch, nF, nRC, L, d_S, st);
+    case 8: return launch_ct_lag<CtV8>(U, pitch, nF, nRC, L, d_S, st);
+    case 9: return launch_ct_lag<CtV9>(U, pitch, nF, nRC, L, d_S, st);
+    case 10: return launch_ct_lag<CtV10>(U, pitch, nF, nRC, L, d_S, st);
+    case 11: return launch_ct_lag<CtV11>(U, pitch, nF, nRC, L, d_S, st);
+    case 12: return launch_ct_lag<CtV12>(U, pitch, nF, nRC, L, d_S, st);
     default: break;
   }
   sr_set_error("sr_ct_lag_sums_variant: unknown variant %d (have %d)", variant, kNumVariants);
@@ -299,7 +379,8 @@ extern "C" int sr_ct_lag_sums_variant(const void* d_packed, long long pitch, int
 
 extern "C" int sr_ct_lag_sums(const void* d_packed, long long pitch, int nC, long long nF, int nR, long long L,
                               double* d_S, void* stream) {
-  return sr_ct_lag_sums_variant(d_packed, pitch, nC, nF, nR, L, d_S, kDefaultVariant, stream);
+  return sr_ct_lag_sums_variant(d_packed, pitch, nC, nF, nR, L, d_S, nF < kShortFrames ? kShortVariant : kLongVariant,
+                                stream);
 }
 
 extern "C" int sr_ct_palmer_finalize(const double* d_S, int nC, long long nF, int nR, long long L, float* d_Ct,
@@ -326,7 +407,7 @@ extern "C" int sr_ct_palmer_device(const float* d_vecs, int nC, long long nF, in
   const long long L = nF / 2;
   char* ws = (char*)d_workspace;
   void* packed = ws;
-  double* S = (double*)(ws + sr_round_up((long long)((size_t)nR * nC * pitch * 16), 256));
+  double* S = (double*)(ws + sr_round_up((long long)((size_t)nR * nC * pitch * 12), 256));
   int rc = sr_pack_vectors_f32(d_vecs, nC, nF, nR, nullptr, packed, pitch, stream);
   if (rc) return rc;
   rc = sr_ct_lag_sums(packed, pitch, nC, nF, nR, L, S, stream);

@@ -2,16 +2,23 @@
 // Reference arithmetic: calculate-Ct-from-traj.py:567 (rotate_vector_simd), :588 (gm.xyz_to_rtp),
 // :600-626 (transpose, cos(theta), np.histogramdd with bins (nbx, nby) over ((-pi,pi),(-1,1))).
 //
-// Bit-exact counts without reproducing NumPy's libm: the kernel decides a bin only when the sample is
-// provably farther than `tol` from every bin edge -- phi through the sign of the cross product with the
-// tabulated edge directions, cos(theta) by comparing z|z| with e|e| r^2 -- and otherwise appends the
-// sample index to an "ambiguous" list that the host re-bins with the reference's own NumPy formula.
-// tol is ~1e-11 for the float64 (rotated) path and a few float32 ulps for the unrotated float32 path.
+// Bit-exact counts without reproducing NumPy's libm, in two passes:
+//   1. sphere_hist_kernel (hot, FP32): rotates, proposes a bin and accepts it only if the sample is farther
+//      than a float32 margin from all four edges of that bin -- phi through the sign of the cross products
+//      with the tabulated edge directions, cos(theta) by direct comparison.  Misses (~1e-4 of the samples)
+//      are appended to a retry list.
+//   2. sphere_hist_resolve_kernel (rare, FP64): re-examines the retry list with the same tests in double
+//      precision and a ~1e-11 margin (rotated stream), or drops NaN / zero vectors (float32 reference stream).
+//      What is still undecided keeps its sample id in the list for the host, which re-bins those few samples
+//      with the reference's own NumPy formula; everything else in the list is overwritten with -1.
 #include "common.cuh"
+#include <algorithm>
 
 namespace {
 
-constexpr int kHistThreads = 512;
+constexpr int kHistThreads = 384;   // threads per CTA (2 CTAs per SM: 85 registers per thread)
+constexpr int kHistGroup = 16;      // vectors per CTA (4 per thread)
+constexpr int kHistFP = kHistThreads / 4;   // frames covered by one pass of the CTA
 
 struct HistParams {
   double R[9];        // rotation matrix (row major), identity when no rotation
@@ -71,95 +78,33 @@ __device__ __forceinline__ int classify(double x, double y, double z, const Slow
   return 0;
 }
 
-// FP32 fast path.  Returns the flat bin, or -1 when the sample is within the fast-path margin of a bin edge
-// (or degenerate) and has to be re-examined.  The margin covers the float32 rounding of the rotated
-// coordinates (fphi_abs, absolute, rotated path) or the reference's own float32 arctan2/arccos/cos error
-// (fphi_rel, relative to the xy-projection, unrotated path).
-struct FastParams { float fphi_abs, fphi_rel, fcos; int nbx, nby; };
-
-__device__ __forceinline__ int fast_classify(float x, float y, float z, const FastParams p,
-                                             const float4* __restrict__ sh_edge /* (cos_i, sin_i, cos_i+1, sin_i+1) */) {
-  // NaN, zero, huge or polar vectors need no explicit test: they fail the margin comparisons below
-  // (rsqrtf(0) = inf -> cf = NaN; rho1 = 0 -> |cross| = 0 < mphi) and drop to the slow path.
-  const float r2 = fmaf(x, x, fmaf(y, y, z * z));
-  const float ax = fabsf(x), ay = fabsf(y);
-  const float rho1 = ax + ay;
-  // phi candidate from a degree-11 odd minimax polynomial of atan on [0,1] (max error 1.8e-6 rad)
-  const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
-  const float t = __fdividef(mn, mx), t2 = t * t;
-  float a = fmaf(t2, -0.01171912346035242f, 0.052647337317466736f);
-  a = fmaf(t2, a, -0.1164264902472496f);
-  a = fmaf(t2, a, 0.19354039430618286f);
-  a = fmaf(t2, a, -0.33262282609939575f);
-  a = fmaf(t2, a, 0.9999772310256958f) * t;
-  if (ay > ax) a = 1.57079632679f - a;
-  if (x < 0.f) a = 3.14159265359f - a;
-  if (y < 0.f) a = -a;
-  int i = (int)floorf((a + 3.14159265359f) * (p.nbx * 0.159154943f));
-  i = max(0, min(p.nbx - 1, i));
-  const float4 e = sh_edge[i];
-  const float mphi = fmaf(p.fphi_rel, rho1, p.fphi_abs * (rho1 + fabsf(z))) + 1e-30f;
-  const float clo = fmaf(e.x, y, -e.y * x);   // rho sin(phi - e_i)
-  const float chi = fmaf(e.z, y, -e.w * x);   // rho sin(phi - e_{i+1})
-  const bool ok_phi = (clo >= mphi) && (chi <= -mphi);
-  // cos(theta)
-  const float cf = z * rsqrtf(r2);
-  const float wbin = 2.0f / p.nby;
-  int j = (int)floorf((cf + 1.0f) * (0.5f * p.nby));
-  j = max(0, min(p.nby - 1, j));
-  const float elo = fmaf((float)j, wbin, -1.0f), ehi = elo + wbin;
-  const bool ok_cos = (cf - elo >= p.fcos) && (ehi - cf >= p.fcos);   // NaN compares false
-  return (ok_phi && ok_cos) ? i * p.nby + j : -1;
-}
-
-// Rare path, kept out of line so the hot loop stays small: FP64 re-examination (rotated stream) or hand-over
-// to the host (float32 reference stream), NaN / zero vectors dropped as np.histogramdd drops them.
-__device__ __noinline__ void slow_sample(float vx, float vy, float vz, int f32_reference, double r0, double r1, double r2,
-                                         double r3, double r4, double r5, double r6, double r7, double r8,
-                                         double tol_phi, double tol_cos, int nbx, int nby,
-                                         const double2* __restrict__ edge_dir, const double* __restrict__ edge_cos,
-                                         unsigned int* sh_vec_hist, long long sample_idx, long long* __restrict__ amb_idx,
-                                         int amb_capacity, int* __restrict__ amb_count) {
-  int bin = 0, cls;
-  if (f32_reference) {
-    const float n2 = vx * vx + vy * vy + vz * vz;
-    cls = (n2 != n2 || n2 == 0.f) ? 1 : 2;
-  } else {
-    const double dx = vx, dy = vy, dz = vz;
-    SlowParams sp; sp.tol_phi = tol_phi; sp.tol_cos = tol_cos; sp.nbx = nbx; sp.nby = nby;
-    cls = classify(r0 * dx + r1 * dy + r2 * dz, r3 * dx + r4 * dy + r5 * dz, r6 * dx + r7 * dy + r8 * dz, sp, edge_dir,
-                   edge_cos, bin);
-  }
-  if (cls == 0) {
-    atomicAdd(&sh_vec_hist[bin >> 1], 1u << ((bin & 1) << 4));
-  } else if (cls == 2) {
-    const int slot = atomicAdd(amb_count, 1);
-    if (slot < amb_capacity) amb_idx[slot] = sample_idx;
-  }
-}
-
-constexpr int kHistU = 4;
-
-// grid.x = vector groups (fastest, so CTAs sharing a frame range run together and the 64-byte DRAM blocks
-// that straddle two groups are fetched once), grid.y = frame blocks.  A CTA owns `group` = 1 << gshift
-// vectors; thread t always works on vector t & (group-1), so its shared-memory histogram base and its global
-// pointer stride are loop invariants.  Bins are privatised in shared memory as packed 16-bit counters
-// (an even number of bins per vector; a CTA sees < 65536 frames).
+// FP32 fast path margins.  fphi_abs covers the float32 rounding of the rotated coordinates (absolute, rotated
+// path); fphi_rel / fcos the reference's own float32 arctan2/arccos/cos error (unrotated path).
+//
+// Hot kernel.  grid.x = vector groups (fastest, so CTAs sharing a frame range run together and the 64-byte
+// DRAM blocks that straddle two groups are fetched once), grid.y = frame blocks.  A CTA owns kHistGroup
+// vectors; thread t works on the four vectors 4*(t&3) .. +3 of frame t>>2 (+128 per pass), i.e. on 48
+// contiguous bytes of the reference's AoS layout -- three LDG.128 when a frame row is a multiple of 16 bytes
+// (nR % 4 == 0), twelve scalar loads otherwise -- and always has the next pass's 48 bytes in flight while it
+// classifies the current ones.  Bins are privatised in shared memory as packed 16-bit counters (an even
+// number of bins per vector; a CTA sees < 65536 frames) and flushed with global atomics at the end.
+template <bool VEC4>
 __global__ void __launch_bounds__(kHistThreads, 2)
-sphere_hist_kernel(const float* __restrict__ vecs, long long nFrames, int nR, int gshift, int framesPerBlock,
-                   HistParams p, const double2* __restrict__ edge_dir, const double* __restrict__ edge_cos,
+sphere_hist_kernel(const float* __restrict__ vecs, long long nFrames, int nR, int framesPerBlock,
+                   HistParams p, const double2* __restrict__ edge_dir,
                    unsigned int* __restrict__ counts, long long* __restrict__ amb_idx, int amb_capacity,
                    int* __restrict__ amb_count) {
-  extern __shared__ unsigned int sh_raw[];
-  float4* sh_edge = reinterpret_cast<float4*>(sh_raw);
-  unsigned int* sh_hist = sh_raw + 4 * p.nbx;
-  const int nbins = p.nbx * p.nby;
+  extern __shared__ __align__(16) unsigned int sh_raw[];
+  float4* const sh_edge = reinterpret_cast<float4*>(sh_raw);
+  unsigned int* const sh_hist = sh_raw + 4 * p.nbx;
+  const int nbx = p.nbx, nby = p.nby;
+  const int nbins = nbx * nby;
   const int wordsPerVec = (nbins + 1) >> 1;
-  const int group = 1 << gshift;
-  const int r0 = blockIdx.x * group;
-  const int nv = min(group, nR - r0);
-  for (int i = threadIdx.x; i < nv * wordsPerVec; i += kHistThreads) sh_hist[i] = 0u;
-  for (int i = threadIdx.x; i < p.nbx; i += kHistThreads) {
+  const int tid = threadIdx.x;
+  const int r0 = blockIdx.x * kHistGroup;
+  const int nv = min(kHistGroup, nR - r0);
+  for (int i = tid; i < nv * wordsPerVec; i += kHistThreads) sh_hist[i] = 0u;
+  for (int i = tid; i < nbx; i += kHistThreads) {
     const double2 lo = edge_dir[i], hi = edge_dir[i + 1];
     sh_edge[i] = make_float4((float)lo.x, (float)lo.y, (float)hi.x, (float)hi.y);
   }
@@ -167,64 +112,131 @@ sphere_hist_kernel(const float* __restrict__ vecs, long long nFrames, int nR, in
 
   const long long f0 = (long long)blockIdx.y * framesPerBlock;
   const int nfl = (int)min((long long)framesPerBlock, nFrames - f0);
-  const int vl = threadIdx.x & (group - 1);
-  const int FP = kHistThreads >> gshift;          // frames covered by one pass of the CTA
-  const size_t rowStride = (size_t)nR * 3;
-  if (vl < nv) {
-    unsigned int* const myhist = sh_hist + vl * wordsPerVec;
-    const long long sidx0 = f0 * nR + r0 + vl;
-    int fl = threadIdx.x >> gshift;
-    const float* src = vecs + ((size_t)(f0 + fl) * nR + r0 + vl) * 3;
-    FastParams fp;
-    fp.fphi_abs = p.fphi_abs; fp.fphi_rel = p.fphi_rel; fp.fcos = p.fcos; fp.nbx = p.nbx; fp.nby = p.nby;
-    const float q0 = p.Rf[0], q1 = p.Rf[1], q2 = p.Rf[2], q3 = p.Rf[3], q4 = p.Rf[4], q5 = p.Rf[5], q6 = p.Rf[6],
-                q7 = p.Rf[7], q8 = p.Rf[8];
-    auto fast = [&](float vx, float vy, float vz) {
+  const int quad = tid & 3;
+  const int nvq = max(0, min(4, nv - 4 * quad));            // valid vectors of this thread
+  int fl = tid >> 2;
+  const uint32_t edge_addr = sr_smem_u32(sh_edge);
+  const uint32_t hist_addr = sr_smem_u32(sh_hist + 4 * quad * wordsPerVec);
+  const uint32_t hist_step = (uint32_t)wordsPerVec * 4u;
+  const float q0 = p.Rf[0], q1 = p.Rf[1], q2 = p.Rf[2], q3 = p.Rf[3], q4 = p.Rf[4], q5 = p.Rf[5], q6 = p.Rf[6],
+              q7 = p.Rf[7], q8 = p.Rf[8];
+  const float fphi_abs = p.fphi_abs, fphi_rel = p.fphi_rel, fcos = p.fcos;
+  const float phi_scale = nbx * 0.159154943f, cos_scale = 0.5f * nby, wbin = 2.0f / nby;
+  const size_t passStride = (size_t)kHistFP * nR * 3;
+  const float* src = vecs + ((size_t)(f0 + fl) * nR + r0 + 4 * quad) * 3;
+  long long sidx = (f0 + fl) * nR + r0 + 4 * quad;          // sample id of this thread's first vector
+  const long long sidxStep = (long long)kHistFP * nR;
+
+  auto load = [&](float (&d)[12], const float* s) {
+    if (VEC4) {
+      const float4* s4 = reinterpret_cast<const float4*>(s);
+      const float4 a = __ldg(s4), b = __ldg(s4 + 1), c = __ldg(s4 + 2);
+      d[0] = a.x; d[1] = a.y; d[2] = a.z; d[3] = a.w; d[4] = b.x; d[5] = b.y; d[6] = b.z; d[7] = b.w;
+      d[8] = c.x; d[9] = c.y; d[10] = c.z; d[11] = c.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 12; ++i) d[i] = (i < 3 * nvq) ? __ldg(s + i) : 0.f;
+    }
+  };
+  auto process = [&](const float (&d)[12], long long sid) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float vx = d[3 * u], vy = d[3 * u + 1], vz = d[3 * u + 2];
       const float x = fmaf(q0, vx, fmaf(q1, vy, q2 * vz));
       const float y = fmaf(q3, vx, fmaf(q4, vy, q5 * vz));
       const float z = fmaf(q6, vx, fmaf(q7, vy, q8 * vz));
-      return fast_classify(x, y, z, fp, sh_edge);
-    };
-    const size_t stepU = (size_t)FP * rowStride;
-    for (; fl + (kHistU - 1) * FP < nfl; fl += kHistU * FP) {
-      float vx[kHistU], vy[kHistU], vz[kHistU];
-      int bin[kHistU];
-#pragma unroll
-      for (int u = 0; u < kHistU; ++u) {
-        vx[u] = __ldg(src); vy[u] = __ldg(src + 1); vz[u] = __ldg(src + 2);
-        src += stepU;
-      }
-      int worst = 0;
-#pragma unroll
-      for (int u = 0; u < kHistU; ++u) { bin[u] = fast(vx[u], vy[u], vz[u]); worst = min(worst, bin[u]); }
-#pragma unroll
-      for (int u = 0; u < kHistU; ++u)
-        if (bin[u] >= 0) atomicAdd(&myhist[bin[u] >> 1], 1u << ((bin[u] & 1) << 4));
-      if (worst < 0) {
-#pragma unroll      // static indices keep vx/vy/vz/bin in registers
-        for (int u = 0; u < kHistU; ++u)
-          if (bin[u] < 0)
-            slow_sample(vx[u], vy[u], vz[u], p.f32_reference, p.R[0], p.R[1], p.R[2], p.R[3], p.R[4], p.R[5], p.R[6], p.R[7],
-                        p.R[8], p.tol_phi, p.tol_cos, p.nbx, p.nby, edge_dir, edge_cos, myhist,
-                        sidx0 + (long long)(fl + u * FP) * nR, amb_idx, amb_capacity, amb_count);
+      // NaN, zero, huge or polar vectors need no explicit test: they fail the margin comparisons below
+      // (rsqrtf(0) = inf -> cf = NaN; rho1 = 0 -> |cross| = 0 < mphi) and go to the retry list.
+      const float r2 = fmaf(x, x, fmaf(y, y, z * z));
+      const float ax = fabsf(x), ay = fabsf(y);
+      const float rho1 = ax + ay;
+      // phi candidate from a degree-11 odd minimax polynomial of atan on [0,1] (max error 1.8e-6 rad)
+      const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+      const float t = __fdividef(mn, mx), t2 = t * t;
+      float a = fmaf(t2, -0.01171912346035242f, 0.052647337317466736f);
+      a = fmaf(t2, a, -0.1164264902472496f);
+      a = fmaf(t2, a, 0.19354039430618286f);
+      a = fmaf(t2, a, -0.33262282609939575f);
+      a = fmaf(t2, a, 0.9999772310256958f) * t;
+      if (ay > ax) a = 1.57079632679f - a;
+      if (x < 0.f) a = 3.14159265359f - a;
+      if (y < 0.f) a = -a;
+      int i = (int)floorf(fmaf(a, phi_scale, 3.14159265359f * phi_scale));
+      i = max(0, min(nbx - 1, i));
+      float4 e;   // (cos e_i, sin e_i, cos e_{i+1}, sin e_{i+1})
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(e.x), "=f"(e.y), "=f"(e.z), "=f"(e.w) : "r"(edge_addr + i * 16));
+      const float mphi = fmaf(fphi_rel, rho1, fphi_abs * (rho1 + fabsf(z))) + 1e-30f;
+      const float clo = fmaf(e.x, y, -e.y * x);   // rho sin(phi - e_i)
+      const float chi = fmaf(e.z, y, -e.w * x);   // rho sin(phi - e_{i+1})
+      const float cf = z * rsqrtf(r2);
+      int j = (int)floorf(fmaf(cf, cos_scale, cos_scale));
+      j = max(0, min(nby - 1, j));
+      const float elo = fmaf((float)j, wbin, -1.0f), ehi = elo + wbin;
+      const bool ok = (clo >= mphi) && (chi <= -mphi) && (cf - elo >= fcos) && (ehi - cf >= fcos);   // NaN compares false
+      const int bin = i * nby + j;
+      if (u < nvq) {
+        if (ok) {
+          asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(hist_addr + u * hist_step + ((bin >> 1) << 2)),
+                       "r"(1u << ((bin & 1) << 4)) : "memory");
+        } else {   // rare: hand the sample to sphere_hist_resolve_kernel
+          const int slot = atomicAdd(amb_count, 1);
+          if (slot < amb_capacity) amb_idx[slot] = sid + u;
+        }
       }
     }
-    for (; fl < nfl; fl += FP, src += stepU) {
-      const float vx = __ldg(src), vy = __ldg(src + 1), vz = __ldg(src + 2);
-      const int bin = fast(vx, vy, vz);
-      if (bin >= 0) atomicAdd(&myhist[bin >> 1], 1u << ((bin & 1) << 4));
-      else slow_sample(vx, vy, vz, p.f32_reference, p.R[0], p.R[1], p.R[2], p.R[3], p.R[4], p.R[5], p.R[6], p.R[7], p.R[8],
-                       p.tol_phi, p.tol_cos, p.nbx, p.nby, edge_dir, edge_cos, myhist, sidx0 + (long long)fl * nR, amb_idx,
-                       amb_capacity, amb_count);
+  };
+
+  if (nvq > 0) {
+    float A[12], B[12];
+    if (fl < nfl) load(A, src);
+    while (fl < nfl) {
+      const bool moreB = fl + kHistFP < nfl;
+      if (moreB) load(B, src + passStride);
+      process(A, sidx);
+      if (!moreB) break;
+      const bool moreA = fl + 2 * kHistFP < nfl;
+      if (moreA) load(A, src + 2 * passStride);
+      process(B, sidx + sidxStep);
+      fl += 2 * kHistFP; src += 2 * passStride; sidx += 2 * sidxStep;
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < nv * wordsPerVec; i += kHistThreads) {
+  for (int i = tid; i < nv * wordsPerVec; i += kHistThreads) {
     const unsigned int w = sh_hist[i];
+    if (w == 0u) continue;
     const int v = i / wordsPerVec, k = i - v * wordsPerVec;
     const long long g = (long long)(r0 + v) * nbins + 2 * k;
     if (w & 0xffffu) atomicAdd(&counts[g], w & 0xffffu);
     if (w >> 16) atomicAdd(&counts[g + 1], w >> 16);
+  }
+}
+
+// Second pass over the fast path's misses (typically ~1e-4 of the samples): FP64 re-examination for the rotated
+// stream, NaN / zero-vector drop for the float32 reference stream.  Resolved entries are overwritten with -1,
+// entries that stay ambiguous keep their sample id for the host tie-break (hist.py::_reference_bins).
+__global__ void __launch_bounds__(256)
+sphere_hist_resolve_kernel(const float* __restrict__ vecs, int nR, HistParams p, const double2* __restrict__ edge_dir,
+                           const double* __restrict__ edge_cos, unsigned int* __restrict__ counts,
+                           long long* __restrict__ amb_idx, int amb_capacity, const int* __restrict__ amb_count) {
+  const int n = min(*amb_count, amb_capacity);
+  const int nbins = p.nbx * p.nby;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+    const long long sidx = amb_idx[e];
+    if (sidx < 0) continue;
+    const float* v = vecs + sidx * 3;
+    const float vx = v[0], vy = v[1], vz = v[2];
+    int bin = 0, cls;
+    if (p.f32_reference) {
+      const float n2 = vx * vx + vy * vy + vz * vz;
+      cls = (n2 != n2 || n2 == 0.f) ? 1 : 2;
+    } else {
+      const double dx = vx, dy = vy, dz = vz;
+      SlowParams sp; sp.tol_phi = p.tol_phi; sp.tol_cos = p.tol_cos; sp.nbx = p.nbx; sp.nby = p.nby;
+      cls = classify(p.R[0] * dx + p.R[1] * dy + p.R[2] * dz, p.R[3] * dx + p.R[4] * dy + p.R[5] * dz,
+                     p.R[6] * dx + p.R[7] * dy + p.R[8] * dz, sp, edge_dir, edge_cos, bin);
+    }
+    if (cls == 0) atomicAdd(&counts[(sidx % nR) * nbins + bin], 1u);
+    if (cls != 2) amb_idx[e] = -1;
   }
 }
 
@@ -238,6 +250,7 @@ extern "C" int sr_sphere_hist(const float* d_vecs, long long nFrames, int nR, co
   SR_REQUIRE(d_vecs && d_edge_table && d_counts && d_amb_idx && d_amb_count, "sr_sphere_hist: null pointer");
   SR_REQUIRE(nFrames > 0 && nR > 0 && nbx > 0 && nby > 0, "sr_sphere_hist: empty shape");
   SR_REQUIRE(tol_phi > 0 && tol_cos > 0, "sr_sphere_hist: tolerances must be positive");
+  SR_REQUIRE(amb_capacity > 0, "sr_sphere_hist: the retry / ambiguous list needs a positive capacity");
   HistParams p;
   p.nbx = nbx; p.nby = nby; p.tol_phi = tol_phi; p.tol_cos = tol_cos;
   double q[4] = {1, 0, 0, 0};
@@ -265,28 +278,32 @@ extern "C" int sr_sphere_hist(const float* d_vecs, long long nFrames, int nR, co
   SR_CUDA(cudaGetDevice(&dev));
   SR_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   SR_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  // two CTAs per SM: at most ~100 KB of privatised 16-bit bins each; group is a power of two <= 16
-  int gshift = 4;
   const size_t wordsPerVec = ((size_t)nbins + 1) / 2;
-  while (gshift > 0 && ((size_t)(1 << gshift) * wordsPerVec) * 4 > (size_t)100 * 1024) --gshift;
-  while (gshift > 0 && (1 << (gshift - 1)) >= nR) --gshift;
-  const int group = 1 << gshift;
-  const size_t smem = (size_t)group * wordsPerVec * 4 + (size_t)nbx * 16;
+  const size_t smem = (size_t)kHistGroup * wordsPerVec * 4 + (size_t)nbx * 16;
   SR_REQUIRE(smem <= (size_t)max_smem, "sr_sphere_hist: %d bins do not fit in shared memory", nbins);
-  SR_CUDA(cudaFuncSetAttribute(sphere_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int nGroups = (nR + group - 1) / group;
-  long long nFB = (6LL * 2 * sms + nGroups - 1) / nGroups;     // ~6 waves of 2 CTAs/SM
+  const int nGroups = (nR + kHistGroup - 1) / kHistGroup;
+  // one wave of 2 CTAs per SM; a CTA must see fewer than 65536 frames (16-bit privatised counters)
+  long long nFB = std::max(1LL, (2LL * sms) / nGroups);
   long long fpb = (nFrames + nFB - 1) / nFB;
-  if (fpb < 64) fpb = 64;
-  if (fpb > 32768) fpb = 32768;                                 // 16-bit counters: fewer than 65536 frames per CTA
+  fpb = std::min(std::max(fpb, (long long)kHistFP), 32768LL);
   nFB = (nFrames + fpb - 1) / fpb;
   SR_REQUIRE(nFB <= 65535, "sr_sphere_hist: %lld frame blocks exceed the grid limit", nFB);
   dim3 grid((unsigned)nGroups, (unsigned)nFB);
   const double2* edge_dir = (const double2*)d_edge_table;
   const double* edge_cos = d_edge_table + 2 * (nbx + 1);
-  sphere_hist_kernel<<<grid, kHistThreads, smem, (cudaStream_t)stream>>>(d_vecs, nFrames, nR, gshift, (int)fpb, p, edge_dir,
-                                                                         edge_cos, d_counts, d_amb_idx, amb_capacity,
-                                                                         d_amb_count);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (nR % 4 == 0 && ((uintptr_t)d_vecs & 15) == 0) {
+    SR_CUDA(cudaFuncSetAttribute(sphere_hist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    sphere_hist_kernel<true><<<grid, kHistThreads, smem, st>>>(d_vecs, nFrames, nR, (int)fpb, p, edge_dir, d_counts,
+                                                              d_amb_idx, amb_capacity, d_amb_count);
+  } else {
+    SR_CUDA(cudaFuncSetAttribute(sphere_hist_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    sphere_hist_kernel<false><<<grid, kHistThreads, smem, st>>>(d_vecs, nFrames, nR, (int)fpb, p, edge_dir, d_counts,
+                                                               d_amb_idx, amb_capacity, d_amb_count);
+  }
+  SR_CUDA(cudaGetLastError());
+  sphere_hist_resolve_kernel<<<sms, 256, 0, st>>>(d_vecs, nR, p, edge_dir, edge_cos, d_counts, d_amb_idx, amb_capacity,
+                                                  d_amb_count);
   SR_CUDA(cudaGetLastError());
   return SR_OK;
 }

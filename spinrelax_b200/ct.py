@@ -83,7 +83,7 @@ def ct_lag_sums_device(vecs):
     nC, nF, nR, _ = _check_4d(vecs)
     L = nF // 2
     pitch = lib.sr_ct_row_pitch(nF)
-    packed = torch.empty((nR, nC, pitch, 4), dtype=torch.float32, device=vecs.device)
+    packed = torch.empty((nR, nC, 3, pitch), dtype=torch.float32, device=vecs.device)
     S = torch.empty((nR, nC, L), dtype=torch.float64, device=vecs.device)
     st = _lib.current_stream_ptr()
     _lib.check(lib.sr_pack_vectors_f32(vecs.data_ptr(), nC, nF, nR, None, packed.data_ptr(), pitch, st),

@@ -93,6 +93,9 @@ class SphereHistogram:
         self.last_ambiguous = n_amb
         if n_amb:
             idx = self.amb_idx[:n_amb]
+            idx = idx[idx >= 0]          # -1 = resolved on the device by sphere_hist_resolve_kernel
+            self.last_ambiguous = int(idx.numel())
+        if n_amb and idx.numel():
             rows = v_dev.reshape(-1, 3)[idx].cpu().numpy()
             idx = idx.cpu().numpy()
             bins = _reference_bins(rows, q_rot, self.edges_phi, self.edges_cos)

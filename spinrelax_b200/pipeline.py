@@ -24,7 +24,7 @@ class CtHistStep:
         self.nbx, self.nby = hist_bins, hist_bins // 2
         self.has_hist = hasattr(self.lib, "sr_sphere_hist") and q_rot is not None
         self.pitch = self.lib.sr_ct_row_pitch(nF)
-        self.packed = torch.empty((nR, nC, self.pitch, 4), dtype=torch.float32, device=self.dev)
+        self.packed = torch.empty((nR, nC, 3, self.pitch), dtype=torch.float32, device=self.dev)
         self.S = torch.empty((nR, nC, self.L), dtype=torch.float64, device=self.dev)
         self.Ct = torch.empty((self.L, nR), dtype=torch.float32, device=self.dev)
         self.dCt = torch.empty((self.L, nR), dtype=torch.float32, device=self.dev)

@@ -94,7 +94,7 @@ def test_ct_known_answers(golden):
     pitch = lib.sr_ct_row_pitch(nF)
     outs = []
     for q in (None, (ctypes.c_double * 4)(0.83, -0.31, 0.22, 0.41)):
-        packed = torch.empty((nR, nC, pitch, 4), dtype=torch.float32, device="cuda")
+        packed = torch.empty((nR, nC, 3, pitch), dtype=torch.float32, device="cuda")
         S = torch.empty((nR, nC, nF // 2), dtype=torch.float64, device="cuda")
         _lib.check(lib.sr_pack_vectors_f32(vt.data_ptr(), nC, nF, nR, q, packed.data_ptr(), pitch, None))
         _lib.check(lib.sr_ct_lag_sums(packed.data_ptr(), pitch, nC, nF, nR, nF // 2, S.data_ptr(), None))

@@ -44,7 +44,7 @@ def main():
     vt = (vt / vt.norm(dim=-1, keepdim=True)).contiguous()
     L = nF // 2
     pitch = lib.sr_ct_row_pitch(nF)
-    packed = torch.empty((nR, nC, pitch, 4), dtype=torch.float32, device="cuda")
+    packed = torch.empty((nR, nC, 3, pitch), dtype=torch.float32, device="cuda")
     S = torch.empty((nR, nC, L), dtype=torch.float64, device="cuda")
     st = _lib.current_stream_ptr()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]

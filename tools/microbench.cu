@@ -92,6 +92,7 @@ __global__ void __launch_bounds__(256, 2) k_p2pattern_lds(float* out, int iters)
   int s = warp * 64;
   float4 areg = smv[lane];
   float4 a = make_float4(0.3f, 0.4f, 0.5f, 0.f), nx = make_float4(0.31f, 0.41f, 0.51f, 0.f);
+  float4 a2 = a, nx2 = nx;
   for (int it = 0; it < iters; ++it) {
     if (MODE == 5 && (it & 1) == 0) areg = smv[(s + lane) & 2047];
 #pragma unroll
@@ -118,6 +119,24 @@ __global__ void __launch_bounds__(256, 2) k_p2pattern_lds(float* out, int iters)
         const float2 axy = *reinterpret_cast<const float2*>(&smv[ia]); a.x = axy.x; a.y = axy.y; a.z = smf[4 * ia + 2];
         const float2 wxy = *reinterpret_cast<const float2*>(&smv[iw]); nx.x = wxy.x; nx.y = wxy.y; nx.z = smf[4 * iw + 2];
       }
+      if (MODE == 10) {  // left vector SoA scalar broadcast, window via SHFL from the neighbour lane
+        const int ia = (s + k) & 2047;
+        a.x = smf[ia]; a.y = smf[4096 + ia]; a.z = smf[8192 + ia];
+        nx.x = __shfl_down_sync(0xffffffffu, wx[k], 1); nx.y = __shfl_down_sync(0xffffffffu, wy[k], 1);
+        nx.z = __shfl_down_sync(0xffffffffu, wz[k], 1);
+        if (lane == 31) { const int iw = ((s + k) & 1023) + o + R; nx.x = smf[iw]; nx.y = smf[4096 + iw]; nx.z = smf[8192 + iw]; }
+      }
+      if (MODE == 11) {  // SoA, two steps per load: LDS.64 for both (R odd: window pairs alternate alignment, emulate with even k only)
+        if ((k & 1) == 0) {
+          const int ia = (s + k) & 2046, iw = (((s + k) & 1022) + o + R) & ~1;
+          const float2 ax2 = *reinterpret_cast<const float2*>(smf + ia), ay2 = *reinterpret_cast<const float2*>(smf + 4096 + ia),
+                       az2 = *reinterpret_cast<const float2*>(smf + 8192 + ia);
+          const float2 wx2 = *reinterpret_cast<const float2*>(smf + iw), wy2 = *reinterpret_cast<const float2*>(smf + 4096 + iw),
+                       wz2 = *reinterpret_cast<const float2*>(smf + 8192 + iw);
+          a.x = ax2.x; a.y = ay2.x; a.z = az2.x; a2.x = ax2.y; a2.y = ay2.y; a2.z = az2.y;
+          nx.x = wx2.x; nx.y = wy2.x; nx.z = wz2.x; nx2.x = wx2.y; nx2.y = wy2.y; nx2.z = wz2.y;
+        } else { a = a2; nx = nx2; }
+      }
       if (MODE == 5) {
         const int src = (k + (it & 1) * R) & 31;
         a.x = __shfl_sync(0xffffffffu, areg.x, src); a.y = __shfl_sync(0xffffffffu, areg.y, src);
@@ -129,8 +148,8 @@ __global__ void __launch_bounds__(256, 2) k_p2pattern_lds(float* out, int iters)
         nx.z = __shfl_down_sync(0xffffffffu, wz[k], 1);
         if (lane == 31) { const float4 t4 = smv[((s + k) & 1023) + o + R]; nx.x = t4.x; nx.y = t4.y; nx.z = t4.z; }
       }
-      if (MODE == 1 || MODE == 3) { nx.x += 1e-7f; }
-      if (MODE == 1 || MODE == 2) { a.x += 1e-8f; }
+      if (MODE == 1 || MODE == 3) { nx.x += 1e-7f; nx.y -= 1e-7f; nx.z += 2e-7f; }
+      if (MODE == 1 || MODE == 2) { a.x += 1e-8f; a.y -= 1e-8f; a.z += 2e-8f; }
 #pragma unroll
       for (int j = 0; j < R; ++j) {
         const int sl = (k + j) % R;
@@ -390,7 +409,7 @@ int main() {
       ms = time_ms([&] { k_p2pattern_lds<15, MODE><<<g2, block, smem>>>(d, it2); });                              \
       pairs = nthr2 * it2 * 15 * 15;                                                                              \
       printf("{\"probe\":\"p2pattern_lds_R15_mode%d\",\"ms\":%.3f,\"pairs_per_s\":%.4g,\"tflops7\":%.2f}\n", MODE, ms, pairs / ms * 1e3, pairs * 7 / ms * 1e-9);
-      LDS_PROBE(0) LDS_PROBE(3) LDS_PROBE(4) LDS_PROBE(5) LDS_PROBE(7) LDS_PROBE(8) LDS_PROBE(9)
+      LDS_PROBE(0) LDS_PROBE(3) LDS_PROBE(4) LDS_PROBE(6) LDS_PROBE(7) LDS_PROBE(10) LDS_PROBE(11)
 #undef LDS_PROBE
     }
   }

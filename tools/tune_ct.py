@@ -16,13 +16,13 @@ L = nF // 2
 v = synth.nh_vectors(nC * nF, nR, seed=17).reshape(nC, nF, nR, 3)
 vt = torch.from_numpy(v).cuda()
 pitch = lib.sr_ct_row_pitch(nF)
-packed = torch.empty((nR, nC, pitch, 4), dtype=torch.float32, device="cuda")
+packed = torch.empty((nR, nC, 3, pitch), dtype=torch.float32, device="cuda")
 S = torch.empty((nR, nC, L), dtype=torch.float64, device="cuda")
 _lib.check(lib.sr_pack_vectors_f32(vt.data_ptr(), nC, nF, nR, None, packed.data_ptr(), pitch, None))
 So = ct_oracle.ct_lag_sums_fft(v[:, :, :2])
 pairs = nR * nC * (L * nF - L * (L + 1) // 2)
 res = {}
-variants = [int(x) for x in os.environ.get("TUNE_VARIANTS", "0,1,2,3,4,5,6,7").split(",")]
+variants = [int(x) for x in os.environ.get("TUNE_VARIANTS", "0,1,2,3,4,5,6,7,8,9,10,11").split(",")]
 for var in variants:
     best = 1e30
     for it in range(3):
