@@ -270,8 +270,8 @@ def run_ours(args):
                 "data": "synthetic", "config": workload_config(world), "clocks": clocks,
                 "e2e": {"value": pairs_gpu * world * e2e_steps / e2e_s, "unit": UNIT,
                         "h2d_bytes_per_step": int(v_np.nbytes), "d2h_bytes_per_step": int(step.d2h_bytes()),
-                        "steps": e2e_steps, "api": "spinrelax_b200.pipeline.CtHistStep.run_host: pinned NumPy in -> H2D -> "
-                        "sr_pack_vectors_f32, sr_ct_lag_sums, sr_ct_palmer_finalize, sr_sphere_hist (C ABI) -> D2H"},
+                        "steps": e2e_steps, "api": "spinrelax_b200.pipeline.CtHistStep.run_host: pinned NumPy in -> per-chunk H2D pipelined with "
+                        "sr_pack_vectors_f32_chunks, sr_ct_lag_sums_chunks -> sr_ct_palmer_finalize, sr_sphere_hist (C ABI) -> D2H"},
                 "gpu_launches": step.launches_per_step() * args.steps, "roofline": roof, "cpu_baseline": cpu}
         print(json.dumps(line))
     if world > 1:

@@ -58,10 +58,20 @@ size_t sr_ct_workspace_bytes(int nC, long long nF, int nR);
 int sr_pack_vectors_f32(const float* d_vecs, int nC, long long nF, int nR, const double* h_q_rot,
                         void* d_packed, long long pitch, void* stream);
 
+/* The same for the chunk range [c0, c0 + nCsub) only: d_vecs_c0 points at chunk c0 of the input, the rows written are
+ * the ones sr_pack_vectors_f32 would write for those chunks.  Lets a host pipeline overlap the H2D copy of chunk
+ * c + 1 with the kernels of chunk c. */
+int sr_pack_vectors_f32_chunks(const float* d_vecs_c0, int nC, int c0, int nCsub, long long nF, int nR,
+                               const double* h_q_rot, void* d_packed, long long pitch, void* stream);
+
 /* K1: lag sums S[(r*nC + c)*L + (delta-1)] = sum_t ( u(t) . u(t+delta) )^2, t in [0, nF-delta),
  * FP32 products with FP64 accumulation.  d_packed is the output of sr_pack_vectors_f32. */
 int sr_ct_lag_sums(const void* d_packed, long long pitch, int nC, long long nF, int nR, long long L,
                    double* d_S, void* stream);
+
+/* K1 restricted to the chunk range [c0, c0 + nCsub); d_packed and d_S are the full buffers. */
+int sr_ct_lag_sums_chunks(const void* d_packed, long long pitch, int nC, int c0, int nCsub, long long nF, int nR,
+                          long long L, double* d_S, void* stream);
 
 /* Same kernel with an explicit tile configuration (tuning / profiling only; 0 .. 7, see csrc/ct.cu). */
 int sr_ct_lag_sums_variant(const void* d_packed, long long pitch, int nC, long long nF, int nR, long long L,
@@ -87,15 +97,39 @@ int sr_ct_palmer_host(const float* h_vecs, int nC, long long nF, int nR, float* 
  * h_q_rot: host pointer to (w,x,y,z) or NULL for no rotation (float32 path of the reference).
  * d_edge_table: 2*(nbx+1) doubles (cos e_i, sin e_i of the phi edges) followed by the nby+1 cos(theta)
  * edges, as np.histogramdd builds them.  Counts are ADDED into d_counts [nR][nbx][nby] (uint32).
- * Samples closer than tol_phi (rad) / tol_cos to a bin edge are not counted; their flat sample index
- * (frame*nR + r) is appended to d_amb_idx (up to amb_capacity; *d_amb_count keeps counting beyond it) so
- * the caller can bin them with the reference's exact NumPy formula -- this is what makes the counts
- * bit-identical to the reference without sharing its libm.
+ * Two launches: the FP32 hot pass counts every sample it can place with a float32 margin and appends the flat
+ * sample index (frame*nR + r) of the others (~1e-4 of the stream) to d_amb_idx (up to amb_capacity;
+ * *d_amb_count keeps counting beyond it, so amb_capacity bounds the retry list, not only the final list); the
+ * FP64 resolve pass then re-examines that list, counts what is farther than tol_phi (rad) / tol_cos from every
+ * bin edge and overwrites those entries with -1.  Entries that are still >= 0 afterwards are samples the caller
+ * must bin with the reference's exact NumPy formula -- this is what makes the counts bit-identical to the
+ * reference without sharing its libm.  A list that was appended to by an earlier call is re-examined against
+ * THIS call's d_vecs, so reset *d_amb_count between different arrays.
  * ---------------------------------------------------------------------------------------------- */
 int sr_sphere_hist_table_doubles(int nbx, int nby);
 int sr_sphere_hist(const float* d_vecs, long long nFrames, int nR, const double* h_q_rot, int nbx, int nby,
                    const double* d_edge_table, double tol_phi, double tol_cos, unsigned int* d_counts,
                    long long* d_amb_idx, int amb_capacity, int* d_amb_count, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * X-H bond vectors from Cartesian coordinates: the step in front of the hot path.
+ * Replaces obtain_XHvecs(), calculate-Ct-from-traj.py:64-86: np.take(xyz, indexH, 1) - np.take(xyz, indexX, 1)
+ * followed by qs.vecnorm_NDarray (transforms3d_supplement.py:40-52; float32, bit-identical to NumPy including
+ * nan_to_num of a zero vector).
+ * d_xyz: (nFrames, nAtoms, 3) float32 (mdtraj's traj.xyz); d_idxH / d_idxX: nR atom indices each (int32);
+ * d_out: (nFrames, nR, 3) float32 unit vectors, the layout calculate_Ct_Palmer's input is built from.
+ * ---------------------------------------------------------------------------------------------- */
+int sr_xh_vectors(const float* d_xyz, long long nFrames, int nAtoms, const int* d_idxH, const int* d_idxX, int nR,
+                  float* d_out, void* stream);
+
+/* The same after trj.center_coordinates(); trj.superpose(ref, frame=0, atom_indices=fit) (:466-467, mdtraj): every
+ * frame is rotated by the proper rotation that minimises the RMSD of its fit atoms to the reference (Horn's
+ * quaternion solution, float64; translations do not matter for bond vectors, so the coordinates are not rewritten).
+ * d_fitIdx: nFit atom indices; d_refFitCentred: (nFit, 3) float64 reference coordinates of those atoms minus their
+ * centroid; d_rot: optional (nFrames, 9) float64 row-major rotation matrices (NULL to skip). */
+int sr_xh_vectors_superposed(const float* d_xyz, long long nFrames, int nAtoms, const int* d_fitIdx,
+                             const double* d_refFitCentred, int nFit, const int* d_idxH, const int* d_idxX, int nR,
+                             float* d_out, double* d_rot, void* stream);
 
 /* Per (block of framesPerBlock frames, vector) sums of x,y,z,xx,xy,xz,yy,yz,zz (FP64) of (nFrames, nR, 3) float32
  * vectors: the reductions behind --vecAvg (calculate-Ct-from-traj.py:579-583) and --S2

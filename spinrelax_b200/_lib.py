@@ -27,6 +27,8 @@ def _declare(lib):
         "sr_ct_workspace_bytes": (sz, [i, ll, i]),
         "sr_pack_vectors_f32": (i, [vp, i, ll, i, dp, vp, ll, vp]),
         "sr_ct_lag_sums": (i, [vp, ll, i, ll, i, ll, vp, vp]),
+        "sr_pack_vectors_f32_chunks": (i, [vp, i, i, i, ll, i, dp, vp, ll, vp]),
+        "sr_ct_lag_sums_chunks": (i, [vp, ll, i, i, i, ll, i, ll, vp, vp]),
         "sr_ct_lag_sums_variant": (i, [vp, ll, i, ll, i, ll, vp, i, vp]),
         "sr_ct_palmer_finalize": (i, [vp, i, ll, i, ll, vp, vp, vp]),
         "sr_ct_palmer_device": (i, [vp, i, ll, i, vp, vp, vp, sz, vp]),
@@ -44,6 +46,8 @@ def _declare(lib):
         "sr_dq_self": (i, [vp, ll, ll, vp, vp]),
         "sr_vec_second_moments": (i, [vp, ll, i, vp, vp]),
         "sr_sphere_hist": (i, [vp, ll, i, dp, i, i, vp, _c.c_double, _c.c_double, vp, vp, i, vp, vp]),
+        "sr_xh_vectors": (i, [vp, ll, i, vp, vp, i, vp, vp]),
+        "sr_xh_vectors_superposed": (i, [vp, ll, i, vp, vp, i, vp, vp, i, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

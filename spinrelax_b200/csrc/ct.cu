@@ -45,7 +45,8 @@ struct CtCfg {
 
 template <class Cfg>
 __global__ void __launch_bounds__(Cfg::NW * 32, Cfg::MINB)
-ct_lag_kernel(const float* __restrict__ U, long long pitch, int nF, int L, int nLT, double* __restrict__ S) {
+ct_lag_kernel(const float* __restrict__ U, long long pitch, int nF, int L, int nLT, int nC, int c0, int nCsub,
+              double* __restrict__ S) {
   constexpr int kR = Cfg::R, kMB = Cfg::MB, kFB = Cfg::FB, kNW = Cfg::NW, kTFW = Cfg::TFW, kTF = Cfg::TF,
                 kTL = Cfg::TL, kTW = Cfg::TW, kStageFloats = Cfg::StageFloats, kStageBytes = Cfg::StageBytes;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -55,8 +56,9 @@ ct_lag_kernel(const float* __restrict__ U, long long pitch, int nF, int L, int n
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long item = blockIdx.x;
-  const long long rc = item / nLT;
+  const long long rcs = item / nLT;                    // row inside the launched chunk range [c0, c0 + nCsub)
   const int lt = (int)(item % nLT);
+  const long long rc = (rcs / nCsub) * nC + c0 + rcs % nCsub;   // row r * nC + c of the full packed stream / S
   const int d0 = lt * kTL;          // smallest lag of this tile
   const int nSteps = nF - d0;       // t in [0, nSteps) has at least one valid pair in this tile
   const int nTiles = (nSteps + kTF - 1) / kTF;
@@ -181,12 +183,16 @@ constexpr int kPF = 64, kPV = 16, kPP = 50, kPT = 256;
 
 template <bool VEC4>
 __global__ void __launch_bounds__(kPT)
-pack_kernel(const float* __restrict__ vecs, int nC, long long nF, int nR, float* __restrict__ U, long long pitch,
+pack_kernel(const float* __restrict__ vecs, int nC, int c0, long long nF, int nR, float* __restrict__ U, long long pitch,
             int do_rot, double qw, double qx, double qy, double qz) {
+  // vecs points at chunk c0 of the input; blockIdx.z counts chunks from there; rows of U are indexed with the
+  // absolute chunk number
   __shared__ float tile[kPF * kPP];
-  const int c = blockIdx.z;
-  const long long f0 = (long long)blockIdx.x * kPF;
-  const int r0 = blockIdx.y * kPV;
+  const int cl = blockIdx.z, c = c0 + blockIdx.z;
+  // blockIdx.x = vector group (fastest): CTAs that share frame rows run together, so the 32-byte sectors that
+  // straddle two groups are fetched from DRAM once
+  const long long f0 = (long long)blockIdx.y * kPF;
+  const int r0 = blockIdx.x * kPV;
   const int nv = min(kPV, nR - r0);
   const int tid = threadIdx.x;
 
@@ -198,7 +204,7 @@ pack_kernel(const float* __restrict__ vecs, int nC, long long nF, int nR, float*
       const long long f = f0 + fl;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (f < nF && k4 < n4)
-        v = __ldg(reinterpret_cast<const float4*>(vecs + (((long long)c * nF + f) * nR + r0) * 3) + k4);
+        v = __ldg(reinterpret_cast<const float4*>(vecs + (((long long)cl * nF + f) * nR + r0) * 3) + k4);
       float* t = tile + fl * kPP + 4 * k4;
       t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w;
     }
@@ -207,7 +213,7 @@ pack_kernel(const float* __restrict__ vecs, int nC, long long nF, int nR, float*
       const int fl = idx / 48, k = idx - fl * 48;
       const long long f = f0 + fl;
       float v = 0.f;
-      if (f < nF && k < 3 * nv) v = __ldg(vecs + (((long long)c * nF + f) * nR + r0) * 3 + k);
+      if (f < nF && k < 3 * nv) v = __ldg(vecs + (((long long)cl * nF + f) * nR + r0) * 3 + k);
       tile[fl * kPP + k] = v;
     }
   }
@@ -245,28 +251,47 @@ pack_kernel(const float* __restrict__ vecs, int nC, long long nF, int nR, float*
 // ------------------------------------------------------------------------------------------------
 // Palmer finalize: chunk means of P2, then mean and std/(sqrt(nC)-1) over chunks (:226-228).
 // ------------------------------------------------------------------------------------------------
+// CTA = tile of 32 lags x 32 vectors: S is read along the lag axis (256-byte runs of doubles), the results
+// are transposed through shared memory so that Ct / dCt rows (lag-major, nR contiguous) are written coalesced.
 __global__ void __launch_bounds__(256)
 ct_finalize_kernel(const double* __restrict__ S, int nC, int nF, int nR, int L, float* __restrict__ Ct,
                    float* __restrict__ dCt) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)L * nR) return;
-  const int r = (int)(idx / L);
-  const int di = (int)(idx - (long long)r * L);   // delta - 1
-  const double nVals = (double)(nF - (di + 1));
-  double mean = 0.0;
-  for (int c = 0; c < nC; ++c) {
-    const double m = -0.5 + 1.5 * (S[((long long)r * nC + c) * L + di] / nVals);
-    mean += m;
+  __shared__ float tm[32][33], ts[32][33];
+  const int d0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int dl = threadIdx.x & 31, rl0 = threadIdx.x >> 5;
+  const int di = d0 + dl;                                   // delta - 1
+  const double inv = di < L ? 1.5 / (double)(nF - (di + 1)) : 0.0;
+#pragma unroll
+  for (int rr = 0; rr < 4; ++rr) {
+    const int rl = rl0 + 8 * rr, r = r0 + rl;
+    float m32 = 0.f, s32 = 0.f;
+    if (r < nR && di < L) {
+      const double* row = S + (long long)r * nC * L + di;
+      double mean = 0.0;
+      for (int c = 0; c < nC; ++c) mean += -0.5 + row[(long long)c * L] * inv;
+      mean /= nC;
+      double var = 0.0;   // two-pass: the chunk means differ by ~1e-2 of their value
+      for (int c = 0; c < nC; ++c) {
+        const double m = -0.5 + row[(long long)c * L] * inv;
+        var += (m - mean) * (m - mean);
+      }
+      var /= nC;
+      m32 = (float)mean;
+      s32 = (float)(sqrt(var) / (sqrt((double)nC) - 1.0));
+    }
+    tm[dl][rl] = m32; ts[dl][rl] = s32;
   }
-  mean /= nC;
-  double var = 0.0;
-  for (int c = 0; c < nC; ++c) {
-    const double m = -0.5 + 1.5 * (S[((long long)r * nC + c) * L + di] / nVals);
-    var += (m - mean) * (m - mean);
+  __syncthreads();
+  const int rl = threadIdx.x & 31;
+#pragma unroll
+  for (int dd = 0; dd < 4; ++dd) {
+    const int dl2 = (threadIdx.x >> 5) + 8 * dd;
+    const int d = d0 + dl2, r = r0 + rl;
+    if (d < L && r < nR) {
+      Ct[(long long)d * nR + r] = tm[dl2][rl];
+      dCt[(long long)d * nR + r] = ts[dl2][rl];
+    }
   }
-  var /= nC;
-  Ct[(long long)di * nR + r] = (float)mean;
-  dCt[(long long)di * nR + r] = (float)(sqrt(var) / (sqrt((double)nC) - 1.0));
 }
 
 // ================================================================================================
@@ -295,12 +320,14 @@ constexpr long long kShortFrames = 8192;
 constexpr int kMaxTF = 1440, kMaxTL = 32 * 21;   // padding must cover the largest tile of any variant
 
 template <class Cfg>
-int launch_ct_lag(const float* U, long long pitch, long long nF, int nRC, long long L, double* S, cudaStream_t st) {
+int launch_ct_lag(const float* U, long long pitch, long long nF, int nR, int nC, int c0, int nCsub, long long L, double* S,
+                  cudaStream_t st) {
   const long long nLT = (L + Cfg::TL) / Cfg::TL;   // tiles start at lag 0: ceil((L + 1) / TL)
-  const long long items = (long long)nRC * nLT;
+  const long long items = (long long)nR * nCsub * nLT;
   SR_REQUIRE(items < (1LL << 31), "sr_ct_lag_sums: %lld work items exceed the grid limit", items);
   SR_CUDA(cudaFuncSetAttribute(ct_lag_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SmemBytes));
-  ct_lag_kernel<Cfg><<<(unsigned)items, Cfg::NW * 32, Cfg::SmemBytes, st>>>(U, pitch, (int)nF, (int)L, (int)nLT, S);
+  ct_lag_kernel<Cfg><<<(unsigned)items, Cfg::NW * 32, Cfg::SmemBytes, st>>>(U, pitch, (int)nF, (int)L, (int)nLT, nC, c0,
+                                                                            nCsub, S);
   SR_CUDA(cudaGetLastError());
   return SR_OK;
 }
@@ -317,13 +344,15 @@ extern "C" size_t sr_ct_workspace_bytes(int nC, long long nF, int nR) {
   return sr_round_up((long long)packed, 256) + sr_round_up((long long)sums, 256);
 }
 
-extern "C" int sr_pack_vectors_f32(const float* d_vecs, int nC, long long nF, int nR, const double* h_q_rot,
-                                   void* d_packed, long long pitch, void* stream) {
-  SR_REQUIRE(d_vecs && d_packed, "sr_pack_vectors_f32: null pointer");
+extern "C" int sr_pack_vectors_f32_chunks(const float* d_vecs_c0, int nC, int c0, int nCsub, long long nF, int nR,
+                                          const double* h_q_rot, void* d_packed, long long pitch, void* stream) {
+  SR_REQUIRE(d_vecs_c0 && d_packed, "sr_pack_vectors_f32: null pointer");
   SR_REQUIRE(nC > 0 && nF > 0 && nR > 0, "sr_pack_vectors_f32: empty shape (nC=%d nF=%lld nR=%d)", nC, nF, nR);
+  SR_REQUIRE(c0 >= 0 && nCsub > 0 && c0 + nCsub <= nC, "sr_pack_vectors_f32: chunk range [%d, %d) outside [0, %d)", c0,
+             c0 + nCsub, nC);
   SR_REQUIRE(pitch >= nF && pitch % 4 == 0, "sr_pack_vectors_f32: pitch %lld must be >= nF %lld and a multiple of 4", pitch, nF);
   SR_REQUIRE(((uintptr_t)d_packed & 15) == 0, "sr_pack_vectors_f32: packed stream must be 16-byte aligned");
-  SR_REQUIRE(nC <= 65535, "sr_pack_vectors_f32: nC %d exceeds grid limit", nC);
+  SR_REQUIRE(nCsub <= 65535, "sr_pack_vectors_f32: %d chunks exceed the grid limit", nCsub);
   double q[4] = {1, 0, 0, 0};
   int do_rot = 0;
   if (h_q_rot) {
@@ -333,19 +362,25 @@ extern "C" int sr_pack_vectors_f32(const float* d_vecs, int nC, long long nF, in
     for (int i = 0; i < 4; ++i) q[i] = h_q_rot[i] / n;   // vecnorm_NDarray(q), transforms3d_supplement.py:280
     do_rot = 1;
   }
-  dim3 grid((unsigned)((pitch + kPF - 1) / kPF), (unsigned)((nR + kPV - 1) / kPV), (unsigned)nC);
-  if (nR % 4 == 0 && ((uintptr_t)d_vecs & 15) == 0)
-    pack_kernel<true><<<grid, kPT, 0, (cudaStream_t)stream>>>(d_vecs, nC, nF, nR, (float*)d_packed, pitch, do_rot, q[0],
-                                                              q[1], q[2], q[3]);
+  SR_REQUIRE((pitch + kPF - 1) / kPF <= 65535, "sr_pack_vectors_f32: %lld frames per chunk exceed the grid limit", nF);
+  dim3 grid((unsigned)((nR + kPV - 1) / kPV), (unsigned)((pitch + kPF - 1) / kPF), (unsigned)nCsub);
+  if (nR % 4 == 0 && ((uintptr_t)d_vecs_c0 & 15) == 0)
+    pack_kernel<true><<<grid, kPT, 0, (cudaStream_t)stream>>>(d_vecs_c0, nC, c0, nF, nR, (float*)d_packed, pitch, do_rot,
+                                                              q[0], q[1], q[2], q[3]);
   else
-    pack_kernel<false><<<grid, kPT, 0, (cudaStream_t)stream>>>(d_vecs, nC, nF, nR, (float*)d_packed, pitch, do_rot, q[0],
-                                                               q[1], q[2], q[3]);
+    pack_kernel<false><<<grid, kPT, 0, (cudaStream_t)stream>>>(d_vecs_c0, nC, c0, nF, nR, (float*)d_packed, pitch, do_rot,
+                                                               q[0], q[1], q[2], q[3]);
   SR_CUDA(cudaGetLastError());
   return SR_OK;
 }
 
-extern "C" int sr_ct_lag_sums_variant(const void* d_packed, long long pitch, int nC, long long nF, int nR, long long L,
-                                      double* d_S, int variant, void* stream) {
+extern "C" int sr_pack_vectors_f32(const float* d_vecs, int nC, long long nF, int nR, const double* h_q_rot,
+                                   void* d_packed, long long pitch, void* stream) {
+  return sr_pack_vectors_f32_chunks(d_vecs, nC, 0, nC, nF, nR, h_q_rot, d_packed, pitch, stream);
+}
+
+static int ct_lag_sums_impl(const void* d_packed, long long pitch, int nC, int c0, int nCsub, long long nF, int nR,
+                            long long L, double* d_S, int variant, void* stream) {
   SR_REQUIRE(d_packed && d_S, "sr_ct_lag_sums: null pointer");
   SR_REQUIRE(nC > 0 && nR > 0 && nF >= 2, "sr_ct_lag_sums: bad shape (nC=%d nF=%lld nR=%d)", nC, nF, nR);
   SR_REQUIRE(L >= 1 && L <= nF - 1, "sr_ct_lag_sums: L=%lld outside [1, nF-1]", L);
@@ -356,40 +391,50 @@ extern "C" int sr_ct_lag_sums_variant(const void* d_packed, long long pitch, int
   SR_REQUIRE(pitch % 4 == 0 && ((uintptr_t)d_packed & 15) == 0, "sr_ct_lag_sums: packed stream must be 16-byte aligned with pitch %% 4 == 0");
   const float* U = (const float*)d_packed;
   cudaStream_t st = (cudaStream_t)stream;
-  const int nRC = nR * nC;
+  SR_REQUIRE(c0 >= 0 && nCsub > 0 && c0 + nCsub <= nC, "sr_ct_lag_sums: chunk range [%d, %d) outside [0, %d)", c0, c0 + nCsub, nC);
   switch (variant) {
-    case 0: return launch_ct_lag<CtV0>(U, pitch, nF, nRC, L, d_S, st);
-    case 1: return launch_ct_lag<CtV1>(U, pitch, nF, nRC, L, d_S, st);
-    case 2: return launch_ct_lag<CtV2>(U, pitch, nF, nRC, L, d_S, st);
-    case 3: return launch_ct_lag<CtV3>(U, pitch, nF, nRC, L, d_S, st);
-    case 4: return launch_ct_lag<CtV4>(U, pitch, nF, nRC, L, d_S, st);
-    case 5: return launch_ct_lag<CtV5>(U, pitch, nF, nRC, L, d_S, st);
-    case 6: return launch_ct_lag<CtV6>(U, pitch, nF, nRC, L, d_S, st);
-    case 7: return launch_ct_lag<CtV7>(U, pitch, nF, nRC, L, d_S, st);
-    case 8: return launch_ct_lag<CtV8>(U, pitch, nF, nRC, L, d_S, st);
-    case 9: return launch_ct_lag<CtV9>(U, pitch, nF, nRC, L, d_S, st);
-    case 10: return launch_ct_lag<CtV10>(U, pitch, nF, nRC, L, d_S, st);
-    case 11: return launch_ct_lag<CtV11>(U, pitch, nF, nRC, L, d_S, st);
-    case 12: return launch_ct_lag<CtV12>(U, pitch, nF, nRC, L, d_S, st);
+    case 0: return launch_ct_lag<CtV0>(U, pitch, nF, nR, nC, c0, nCsub, L, d_S, st);
+    case 1: return launch_ct_lag<CtV1>(U, pitch, nF, nR, nC, c0, nCsub, L, d_S, st);
+    case 2: return launch_ct_lag<CtV2>(U, pitch, nF, nR, nC, c0, nCsub, L, d_S, st);
+    case 3: return launch_ct_lag<CtV3>(U, pitch, nF, nR, nC, c0, nCsub, L, d_S, st);
+    case 4: return launch_ct_lag<CtV4>(U, pitch, nF, nR, nC, c0, nCsub, L, d_S, st);
+    case 5: return launch_ct_lag<CtV5>(U, pitch, nF, nR, nC, c0, nCsub, L, d_S, st);
+    case 6: return launch_ct_lag<CtV6>(U, pitch, nF, nR, nC, c0, nCsub, L, d_S, st);
+    case 7: return launch_ct_lag<CtV7>(U, pitch, nF, nR, nC, c0, nCsub, L, d_S, st);
+    case 8: return launch_ct_lag<CtV8>(U, pitch, nF, nR, nC, c0, nCsub, L, d_S, st);
+    case 9: return launch_ct_lag<CtV9>(U, pitch, nF, nR, nC, c0, nCsub, L, d_S, st);
+    case 10: return launch_ct_lag<CtV10>(U, pitch, nF, nR, nC, c0, nCsub, L, d_S, st);
+    case 11: return launch_ct_lag<CtV11>(U, pitch, nF, nR, nC, c0, nCsub, L, d_S, st);
+    case 12: return launch_ct_lag<CtV12>(U, pitch, nF, nR, nC, c0, nCsub, L, d_S, st);
     default: break;
   }
   sr_set_error("sr_ct_lag_sums_variant: unknown variant %d (have %d)", variant, kNumVariants);
   return SR_ERR_ARG;
 }
 
+extern "C" int sr_ct_lag_sums_variant(const void* d_packed, long long pitch, int nC, long long nF, int nR, long long L,
+                                      double* d_S, int variant, void* stream) {
+  return ct_lag_sums_impl(d_packed, pitch, nC, 0, nC, nF, nR, L, d_S, variant, stream);
+}
+
 extern "C" int sr_ct_lag_sums(const void* d_packed, long long pitch, int nC, long long nF, int nR, long long L,
                               double* d_S, void* stream) {
-  return sr_ct_lag_sums_variant(d_packed, pitch, nC, nF, nR, L, d_S, nF < kShortFrames ? kShortVariant : kLongVariant,
-                                stream);
+  return ct_lag_sums_impl(d_packed, pitch, nC, 0, nC, nF, nR, L, d_S, nF < kShortFrames ? kShortVariant : kLongVariant,
+                          stream);
+}
+
+extern "C" int sr_ct_lag_sums_chunks(const void* d_packed, long long pitch, int nC, int c0, int nCsub, long long nF, int nR,
+                                     long long L, double* d_S, void* stream) {
+  return ct_lag_sums_impl(d_packed, pitch, nC, c0, nCsub, nF, nR, L, d_S,
+                          nF < kShortFrames ? kShortVariant : kLongVariant, stream);
 }
 
 extern "C" int sr_ct_palmer_finalize(const double* d_S, int nC, long long nF, int nR, long long L, float* d_Ct,
                                      float* d_dCt, void* stream) {
   SR_REQUIRE(d_S && d_Ct && d_dCt, "sr_ct_palmer_finalize: null pointer");
   SR_REQUIRE(nC > 0 && nR > 0 && L >= 1 && L < nF, "sr_ct_palmer_finalize: bad shape");
-  const long long n = L * nR;
-  ct_finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_S, nC, (int)nF, nR, (int)L, d_Ct,
-                                                                                    d_dCt);
+  dim3 grid((unsigned)((L + 31) / 32), (unsigned)((nR + 31) / 32));
+  ct_finalize_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_S, nC, (int)nF, nR, (int)L, d_Ct, d_dCt);
   SR_CUDA(cudaGetLastError());
   return SR_OK;
 }

@@ -13,7 +13,10 @@ namespace {
 
 constexpr int kDqThreads = 256;
 constexpr int kDqPerThread = 16;
-constexpr int kDqTile = kDqThreads * kDqPerThread;   // frames per CTA per lag
+constexpr int kDqTile = kDqThreads * kDqPerThread;   // frames per CTA (vec_moments_kernel)
+constexpr int kDqLagTile = 16;                       // lags per CTA (dq_moments_kernel)
+constexpr int kDqFrameTile = 1024;                   // frames per CTA (dq_moments_kernel)
+constexpr int kDqU = 4;                              // q(t + delta) loads in flight per thread (x2: double buffered)
 
 struct Vec3d { double x, y, z; };
 
@@ -28,42 +31,85 @@ __device__ __forceinline__ Vec3d dq_vector(const float4 a, const float4 b) {
   return v;
 }
 
-// grid.x = lagIndex * tilesMax + tile
+// CTA = (tile of 16 entries of the lag list, tile of 1024 frames).  The left quaternions q(t) of the frame tile
+// are converted to double once and staged in shared memory (34 KB), so each of them is reused by the 16 lags;
+// thread (lag j = tid >> 4, frame lane = tid & 15) streams q(t + delta_j) as coalesced float4 (consecutive
+// lags hit the same L1 lines) and keeps its six second-moment sums in registers.  Per pair: 4 F2F + 18
+// FP64 instructions, 16 bytes of L1/L2 traffic.  grid.x = lagTile * tilesMax + frameTile.
 __global__ void __launch_bounds__(kDqThreads)
 dq_moments_kernel(const float4* __restrict__ q, long long N, const long long* __restrict__ lags, int nLags, int nCh,
                   int tilesMax, double* __restrict__ M) {
-  const int li = blockIdx.x / tilesMax;
-  const int tile = blockIdx.x - li * tilesMax;
+  // left quaternions of the frame tile as four planes of doubles (w | x | y | z): a half-warp reads 16
+  // consecutive doubles per plane (one wavefront, broadcast to the other half-warp); an array of double4
+  // would cost 8 wavefronts per LDS.128 (32-byte lane stride) and saturate the shared-memory data pipe
+  extern __shared__ __align__(16) double sh_a[];
+  constexpr int kPlane = kDqFrameTile + 16 * kDqU;
+  const int lt = blockIdx.x / tilesMax;
+  const int tile = blockIdx.x - lt * tilesMax;
+  const long long lo = (long long)tile * kDqFrameTile;
+  const int jl = threadIdx.x >> 4, fl = threadIdx.x & 15;
+  const int li = lt * kDqLagTile + jl;
+  const unsigned halfmask = 0xffffu << (threadIdx.x & 16);
+  // the smallest lag of the tile decides whether this frame tile holds any pair at all
+  long long dmin = lags[lt * kDqLagTile];
+  for (int j = 1; j < kDqLagTile && lt * kDqLagTile + j < nLags; ++j) dmin = min(dmin, lags[lt * kDqLagTile + j]);
+  if (lo >= N - dmin) return;
+  for (int i = threadIdx.x; i < kDqFrameTile + 16 * kDqU; i += kDqThreads) {   // zero tail: see the pipeline below
+    const long long t = lo + i;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t < N && i < kDqFrameTile) a = __ldg(q + t);
+    sh_a[i] = (double)a.x; sh_a[kPlane + i] = (double)a.y; sh_a[2 * kPlane + i] = (double)a.z; sh_a[3 * kPlane + i] = (double)a.w;
+  }
+  __syncthreads();
+  if (li >= nLags) return;
   const long long delta = lags[li];
   const long long n = N - delta;
-  const long long lo = (long long)tile * kDqTile;
   if (lo >= n) return;
-  const long long hi = min(n, lo + kDqTile);
+  const long long hi = min(n, lo + kDqFrameTile);
   const long long nb = (n + nCh - 1) / nCh;   // ceil(n / nchunk), calculate-dq-distribution.py:129
-  __shared__ double red[kDqThreads / 32][6];
+  const float4* __restrict__ qb = q + delta;
 
   for (long long k = lo / nb; k * nb < hi; ++k) {
-    const long long a = max(lo, k * nb), b = min(hi, (k + 1) * nb);
-    double s[6] = {0, 0, 0, 0, 0, 0};
-    for (long long t = a + threadIdx.x; t < b; t += kDqThreads) {
-      const Vec3d v = dq_vector(__ldg(q + t), __ldg(q + t + delta));
-      s[0] = fma(v.x, v.x, s[0]); s[1] = fma(v.x, v.y, s[1]); s[2] = fma(v.x, v.z, s[2]);
-      s[3] = fma(v.y, v.y, s[3]); s[4] = fma(v.y, v.z, s[4]); s[5] = fma(v.z, v.z, s[5]);
+    const long long a0 = max(lo, k * nb), b0 = min(hi, (k + 1) * nb);
+    double s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0, s5 = 0;
+    // software pipeline: the next four q(t + delta) are in flight while the current four are consumed; a zero
+    // quaternion (past the end of the segment) yields v = 0 and needs no predicate
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    long long t = a0 + fl;
+    float4 bn[kDqU];
+#pragma unroll
+    for (int u = 0; u < kDqU; ++u) bn[u] = (t + 16 * u < b0) ? __ldg(qb + t + 16 * u) : zero4;
+    while (t < b0) {
+      float4 bc[kDqU];
+#pragma unroll
+      for (int u = 0; u < kDqU; ++u) bc[u] = bn[u];
+      const long long tn = t + 16 * kDqU;
+#pragma unroll
+      for (int u = 0; u < kDqU; ++u) bn[u] = (tn + 16 * u < b0) ? __ldg(qb + tn + 16 * u) : zero4;
+      const double* ap = sh_a + (t - lo);
+#pragma unroll
+      for (int u = 0; u < kDqU; ++u) {
+        const double4 a = make_double4(ap[16 * u], ap[kPlane + 16 * u], ap[2 * kPlane + 16 * u], ap[3 * kPlane + 16 * u]);
+        const double w2 = bc[u].x, x2 = bc[u].y, y2 = bc[u].z, z2 = bc[u].w;
+        // vector part of conj(a) * b (quat_mult_simd(quat_invert(a), b)); the sign image w >= 0 leaves v v^T unchanged
+        const double vx = fma(a.x, x2, fma(-w2, a.y, fma(a.w, y2, -(a.z * z2))));
+        const double vy = fma(a.x, y2, fma(-w2, a.z, fma(a.y, z2, -(a.w * x2))));
+        const double vz = fma(a.x, z2, fma(-w2, a.w, fma(a.z, x2, -(a.y * y2))));
+        s0 = fma(vx, vx, s0); s1 = fma(vx, vy, s1); s2 = fma(vx, vz, s2);
+        s3 = fma(vy, vy, s3); s4 = fma(vy, vz, s4); s5 = fma(vz, vz, s5);
+      }
+      t = tn;
     }
 #pragma unroll
-    for (int m = 0; m < 6; ++m) s[m] = sr_warp_sum(s[m]);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    __syncthreads();
-    if (lane == 0) {
-#pragma unroll
-      for (int m = 0; m < 6; ++m) red[warp][m] = s[m];
+    for (int o = 8; o > 0; o >>= 1) {
+      s0 += __shfl_xor_sync(halfmask, s0, o); s1 += __shfl_xor_sync(halfmask, s1, o);
+      s2 += __shfl_xor_sync(halfmask, s2, o); s3 += __shfl_xor_sync(halfmask, s3, o);
+      s4 += __shfl_xor_sync(halfmask, s4, o); s5 += __shfl_xor_sync(halfmask, s5, o);
     }
-    __syncthreads();
-    if (threadIdx.x < 6) {
-      double tot = 0.0;
-#pragma unroll
-      for (int w = 0; w < kDqThreads / 32; ++w) tot += red[w][threadIdx.x];
-      atomicAdd(&M[((long long)li * nCh + k) * 6 + threadIdx.x], tot);
+    if (fl == 0) {
+      double* m = M + ((long long)li * nCh + k) * 6;
+      atomicAdd(m + 0, s0); atomicAdd(m + 1, s1); atomicAdd(m + 2, s2);
+      atomicAdd(m + 3, s3); atomicAdd(m + 4, s4); atomicAdd(m + 5, s5);
     }
   }
 }
@@ -124,12 +170,15 @@ extern "C" int sr_dq_moments(const float* d_q, long long N, const long long* d_l
   SR_REQUIRE(d_q && d_lags && d_M, "sr_dq_moments: null pointer");
   SR_REQUIRE(N >= 2 && nLags > 0 && nCh >= 1, "sr_dq_moments: bad shape (N=%lld nLags=%d nCh=%d)", N, nLags, nCh);
   SR_REQUIRE(min_lag >= 1 && min_lag < N, "sr_dq_moments: min_lag %lld outside [1, N)", min_lag);
-  const long long tilesMax = (N - min_lag + kDqTile - 1) / kDqTile;
-  const long long blocks = tilesMax * nLags;
+  const long long tilesMax = (N - min_lag + kDqFrameTile - 1) / kDqFrameTile;
+  const long long lagTiles = (nLags + kDqLagTile - 1) / kDqLagTile;
+  const long long blocks = tilesMax * lagTiles;
   SR_REQUIRE(blocks < (1LL << 31), "sr_dq_moments: %lld blocks exceed the grid limit; split the lag list", blocks);
   SR_CUDA(cudaMemsetAsync(d_M, 0, sizeof(double) * 6 * (size_t)nLags * nCh, (cudaStream_t)stream));
-  dq_moments_kernel<<<(unsigned)blocks, kDqThreads, 0, (cudaStream_t)stream>>>((const float4*)d_q, N, d_lags, nLags, nCh,
-                                                                              (int)tilesMax, d_M);
+  const int smem = (kDqFrameTile + 16 * kDqU) * (int)sizeof(double4);
+  SR_CUDA(cudaFuncSetAttribute(dq_moments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  dq_moments_kernel<<<(unsigned)blocks, kDqThreads, smem, (cudaStream_t)stream>>>((const float4*)d_q, N, d_lags, nLags,
+                                                                                 nCh, (int)tilesMax, d_M);
   SR_CUDA(cudaGetLastError());
   return SR_OK;
 }

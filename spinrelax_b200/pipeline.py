@@ -32,7 +32,7 @@ class CtHistStep:
             from . import hist as _hist
             self._hist = _hist.SphereHistogram(nR, self.nbx, device=self.dev)
         self._events = {}
-        self._launches = 3 + (1 if self.has_hist else 0)
+        self._launches = 3 + (2 if self.has_hist else 0)   # pack, lag sums, finalize (+ histogram, resolve)
 
     # -------------------------------------------------------------------------------------------
     def _timed(self, name, fn, on):
@@ -72,13 +72,57 @@ class CtHistStep:
         return self.Ct, self.dCt, hist
 
     def run_host(self, v_np):
-        """Public host-buffer path: NumPy (nC, nF, nR, 3) float32 in, NumPy out.  One H2D of the vectors
-        (pinned memory is copied asynchronously), the same kernels as run_device, D2H of Ct, dCt, counts."""
-        torch = self.torch
+        """Public host-buffer path: NumPy (nC, nF, nR, 3) float32 in, NumPy out.
+
+        Chunks are contiguous in the reference layout, so the H2D copy is pipelined with the kernels: chunk
+        0 is copied first and its K2 / K1 run while the remaining chunks are copied on a side stream
+        (asynchronously when the caller's array is pinned; sr_pack_vectors_f32_chunks, sr_ct_lag_sums_chunks).
+        Finalize, the histogram and the D2H of Ct, dCt and the counts follow once the last chunk is done.  The
+        returned Ct / dCt are views of a pinned staging buffer that the next call overwrites."""
+        torch, lib = self.torch, self.lib
+        nC, nF, nR, L = self.nC, self.nF, self.nR, self.L
         v = np.ascontiguousarray(v_np, dtype=np.float32)
-        v_dev = torch.from_numpy(v).to(self.dev, non_blocking=True)
-        Ct, dCt, hist = self.run_device(v_dev)
-        out = torch.stack((Ct, dCt)).cpu().numpy()
+        if v.shape != (nC, nF, nR, 3):
+            raise _lib.SpinRelaxError("run_host: expected shape %s, got %s" % ((nC, nF, nR, 3), v.shape))
+        v_host = torch.from_numpy(v)
+        if getattr(self, "_v_dev", None) is None:
+            self._v_dev = torch.empty((nC, nF, nR, 3), dtype=torch.float32, device=self.dev)
+            self._copy_stream = torch.cuda.Stream(device=self.dev)
+        v_dev = self._v_dev
+        main = torch.cuda.current_stream(self.dev)
+        self._copy_stream.wait_stream(main)            # the previous step may still be reading v_dev
+        # two stages: chunk 0 alone, then the rest in one launch (every extra launch costs a tail of ~1 wave)
+        groups = [(0, 1)] + ([(1, nC - 1)] if nC > 1 else [])
+        ready = []
+        with torch.cuda.stream(self._copy_stream):
+            for c0, n in groups:
+                v_dev[c0:c0 + n].copy_(v_host[c0:c0 + n], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self._copy_stream)
+                ready.append(ev)
+        st = _lib.current_stream_ptr()
+        for (c0, n), ev in zip(groups, ready):
+            main.wait_event(ev)
+            _lib.check(lib.sr_pack_vectors_f32_chunks(v_dev[c0].data_ptr(), nC, c0, n, nF, nR, None, self.packed.data_ptr(),
+                                                      self.pitch, st), "sr_pack_vectors_f32_chunks")
+            _lib.check(lib.sr_ct_lag_sums_chunks(self.packed.data_ptr(), self.pitch, nC, c0, n, nF, nR, L,
+                                                 self.S.data_ptr(), st), "sr_ct_lag_sums_chunks")
+        _lib.check(lib.sr_ct_palmer_finalize(self.S.data_ptr(), nC, nF, nR, L, self.Ct.data_ptr(), self.dCt.data_ptr(), st),
+                   "sr_ct_palmer_finalize")
+        if getattr(self, "_out_host", None) is None:
+            self._out_host = torch.empty((2, L, nR), dtype=torch.float32).pin_memory()
+        self._out_host[0].copy_(self.Ct, non_blocking=True)      # D2H overlaps the histogram pass
+        self._out_host[1].copy_(self.dCt, non_blocking=True)
+        hist = None
+        if self.has_hist:
+            self._hist.accumulate_device(v_dev.view(nC * nF, nR, 3), self.q_rot, reset=True)
+            hist = self._hist.finish(v_dev, self.q_rot)
+        if self.world > 1:
+            from . import shard
+            both = torch.cat((self.Ct, self.dCt), dim=0)
+            self.gathered = shard.gather_columns(both, self.nR * self.world, dst=0)
+        main.synchronize()
+        out = self._out_host.numpy()          # pinned staging buffer, overwritten by the next call
         if hist is not None:
             hist = hist.astype(np.float64)
         return out[0], out[1], hist

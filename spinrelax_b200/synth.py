@@ -89,3 +89,38 @@ def write_plumed_quaternions(path, q, dt=10.0):
         fp.write("#! FIELDS time q.w q.x q.y q.z\n")
         for i in range(len(q)):
             fp.write("%f %.9g %.9g %.9g %.9g\n" % (i * dt, q[i, 0], q[i, 1], q[i, 2], q[i, 3]))
+
+
+def backbone_trajectory(n_frames, n_res, seed=BASE_SEED + 21, tumbling_sigma=0.02, noise=0.005, dt=10.0):
+    """Synthetic protein-like Cartesian trajectory for the front end (obtain_XHvecs + superposition).
+
+    Five atoms per residue in the order N, H, CA, C, O (nm).  A fixed random-coil CA trace (0.38 nm steps) carries
+    rigid backbone atoms; the amide H sits 0.102 nm from N along a synthetic N-H unit vector (`nh_vectors`), every
+    atom gets Gaussian positional noise, and the whole molecule tumbles (rotational random walk) and drifts.
+    Returns (xyz (frames, 5 n_res, 3) float32, selections dict, ref_xyz (5 n_res, 3) float32 = noise-free,
+    un-tumbled structure with the equilibrium N-H directions).
+    """
+    rng = np.random.default_rng(seed)
+    steps = _unit(rng.standard_normal((n_res, 3))) * 0.38
+    ca = np.cumsum(steps, axis=0)
+    off = rng.standard_normal((n_res, 3, 3)) * 0.08                      # N, C, O offsets from CA
+    nh = nh_vectors(n_frames, n_res, seed=seed + 1, dt=dt).astype(np.float64)
+    base = np.empty((n_res, 5, 3))
+    base[:, 0] = ca + off[:, 0]
+    base[:, 2] = ca
+    base[:, 3] = ca + off[:, 1]
+    base[:, 4] = ca + off[:, 2]
+    xyz = np.repeat(base[None], n_frames, axis=0)
+    xyz[:, :, 1] = xyz[:, :, 0] + 0.102 * nh
+    xyz += rng.standard_normal(xyz.shape) * noise
+    xyz = xyz.reshape(n_frames, n_res * 5, 3)
+    xyz -= xyz.mean(axis=1, keepdims=True)
+    q = quaternion_walk(n_frames, seed=seed + 2, sigma=(tumbling_sigma,) * 3, dtype=np.float64)
+    xyz = rotate_by_quats(xyz, q) + np.cumsum(rng.standard_normal((n_frames, 1, 3)) * 0.01, axis=0)
+    ref = base.copy()
+    ref[:, 1] = ref[:, 0] + 0.102 * _unit(nh.mean(axis=0))
+    ref = ref.reshape(n_res * 5, 3)
+    idx = np.arange(n_res) * 5
+    sel = {"name N and not resname PRO": idx, "name H": idx + 1, "name CA": idx + 2,
+           "custom occupancy": np.sort(np.concatenate((idx, idx + 2, idx + 3)))}
+    return xyz.astype(np.float32), sel, ref.astype(np.float32)

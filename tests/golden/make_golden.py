@@ -80,6 +80,31 @@ def _away_from_edges(v, q, nbx, margin):
     return v[ok]
 
 
+class _FakeTopology:
+    """Stand-in for mdtraj's Topology.select: named index lists (mdtraj itself is absent from the image)."""
+
+    def __init__(self, sel):
+        self.sel = sel
+
+    def select(self, txt):
+        return self.sel[txt]
+
+
+class _FakeTraj:
+    def __init__(self, xyz, sel):
+        self.xyz, self.topology = xyz, _FakeTopology(sel)
+
+
+def golden_traj(refct):
+    # the REAL obtain_XHvecs (calculate-Ct-from-traj.py:64-86) on a stand-in trajectory object
+    xyz, sel, ref = synth.backbone_trajectory(40, 12, seed=synth.BASE_SEED + 21)
+    xyz[3, sel["name H"][2]] = xyz[3, sel["name N and not resname PRO"][2]]      # zero vector -> nan_to_num path
+    with quiet():
+        vec = refct.obtain_XHvecs(_FakeTraj(xyz, sel), "name H", "name N and not resname PRO")
+    save("traj.npz", xyz=xyz, ref=ref, indexH=sel["name H"], indexX=sel["name N and not resname PRO"],
+         fit=sel["custom occupancy"], vecXH=vec)
+
+
 def golden_hist(refct):
     qs = ref_loader.module("transforms3d_supplement")
     gm = ref_loader.module("general_maths")
@@ -312,6 +337,7 @@ def main():
     refct = ref_loader.script("calculate-Ct-from-traj.py")
     refdq = ref_loader.script("calculate-dq-distribution.py")
     golden_ct(refct)
+    golden_traj(refct)
     golden_hist(refct)
     golden_dq(refdq)
     golden_fit()

@@ -181,3 +181,24 @@ def test_cli_ct_end_to_end(tmp_path, golden):
     with pytest.raises(SystemExit) as e:
         cli_ct.main(["-f", str(tmp_path / "a.npy"), "--vecRot", "1 1 0 0"])
     assert e.value.code == 23
+
+
+def test_pipeline_host_path_matches_device_path():
+    """CtHistStep.run_host (per-chunk H2D pipelined with K2/K1 through the *_chunks entry points) must give
+    exactly what the whole-array device path gives, and both must match the oracle."""
+    import torch
+    from spinrelax_b200 import pipeline, synth
+    nC, nF, nR = 3, 9000, 8
+    q = (0.83, -0.31, 0.22, 0.41)
+    v4 = synth.nh_vectors(nC * nF, nR, seed=77).reshape(nC, nF, nR, 3)
+    step = pipeline.CtHistStep(nC, nF, nR, q_rot=q)
+    Ct_d, dCt_d, hist_d = step.run_device(torch.from_numpy(v4).cuda())
+    Ct_d, dCt_d = Ct_d.cpu().numpy().copy(), dCt_d.cpu().numpy().copy()
+    for _ in range(2):                                   # second call reuses the staging buffer and side stream
+        Ct_h, dCt_h, hist_h = step.run_host(v4)
+    assert np.array_equal(Ct_h, Ct_d) and np.array_equal(dCt_h, dCt_d, equal_nan=True)
+    assert np.array_equal(hist_h, hist_d)
+    oCt, odCt = ct_oracle.ct_palmer(v4.astype(np.float64))
+    assert rel_err(Ct_h, oCt) < RTOL_CT
+    ohist, _ = ct_oracle.sphere_histogram(v4.reshape(nC * nF, nR, 3), np.array(q))
+    assert np.array_equal(hist_h, ohist)

@@ -168,3 +168,27 @@ def test_jomega_matches_reference_ufunc(golden):
     assert f32.dtype == np.float32 and np.array_equal(f32, g["jomega_f32"])
     with np.errstate(all="ignore"):
         assert np.isnan(sd_oracle.jomega(0.0, 0.0)) and sd_oracle.jomega(4.0, 0.0) == 0.25
+
+
+def test_traj_oracle_matches_reference(golden):
+    """obtain_XHvecs restatement against the reference's own function (incl. the zero-vector nan_to_num case);
+    the Kabsch restatement (mdtraj boundary, unpinned) must at least be a proper, optimal rotation."""
+    from oracle import traj_oracle
+    g = golden("traj.npz")
+    v = traj_oracle.xh_vectors(g["xyz"], g["indexH"], g["indexX"])
+    assert v.dtype == np.float32 and np.array_equal(v, g["vecXH"])
+    assert np.array_equal(g["vecXH"][3, 2], np.zeros(3, dtype=np.float32))
+    R = traj_oracle.kabsch_rotations(g["xyz"], g["ref"], g["fit"])
+    assert np.max(np.abs(np.linalg.det(R) - 1.0)) < 1e-12
+    x = g["xyz"][:, g["fit"]].astype(np.float64)
+    x -= x.mean(axis=1, keepdims=True)
+    y = g["ref"][g["fit"]].astype(np.float64)
+    y -= y.mean(axis=0)
+    rmsd = np.sqrt(((np.einsum("fab,fib->fia", R, x) - y[None]) ** 2).sum(-1).mean(-1))
+    rng = np.random.default_rng(0)
+    for _ in range(5):                                   # any perturbed rotation is worse
+        w = rng.standard_normal(3) * 1e-3
+        K = np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]])
+        Rp = R @ (np.eye(3) + K + 0.5 * K @ K)
+        rp = np.sqrt(((np.einsum("fab,fib->fia", Rp, x) - y[None]) ** 2).sum(-1).mean(-1))
+        assert np.all(rp >= rmsd - 1e-12)
