@@ -3,11 +3,17 @@
     python -m spinrelax_b200.cli_ct -s ref.pdb -f vecs.npy [vecs2.npy ...] --dt 10 --tau 5000 -o rotdif \
            --vecRot "qw qx qy qz" --vecHist --binary --vecAvg --S2 --Ct
 
-Flags and defaults are the reference's (:303-345).  What is NOT reproduced is the mdtraj front end
-(trajectory reading, centring, superposition, atom selections, :396-498 -- out of scope):
-`-f` takes the unit X-H vector trajectories themselves, one `.npy` (frames, bonds, 3) array -- or `.npz` with
-`vecs` [, `vecs_unfitted`, `names`, `dt`] -- per trajectory, i.e. exactly what obtain_XHvecs (:64-86) returns
-after the fit.  Everything downstream is the reference's flow: reformat by tau (:513-516), C(t) (:527-531),
+Flags and defaults are the reference's (:303-345).  What is NOT reproduced is mdtraj itself (trajectory file
+formats and the atom-selection language, :396-498 -- out of scope).  `-f` takes, per
+trajectory, either
+  * the unit X-H vector trajectory: a `.npy` (frames, bonds, 3) array or an `.npz` with `vecs` [, `vecs_unfitted`,
+    `names`, `dt`], i.e. exactly what obtain_XHvecs (:64-86) returns after the fit; or
+  * Cartesian coordinates: an `.npz` with `xyz` (frames, atoms, 3), `indexH`, `indexX` [, `fit`, `names`, `dt`]
+    (the index arrays mdtraj's `topology.select(--Hsel / --Xsel / --fitsel)` would return).  The vectors are then
+    extracted on the GPU (spinrelax_b200.traj, :83-84) before and after the least-squares superposition onto the
+    reference given with `-s` (`.npy` (atoms, 3) or `.npz` with `xyz`; default: the trajectory's first frame), which
+    is what `trj.center_coordinates(); trj.superpose(ref, frame=0, atom_indices=fit_indices)` (:466-467) does.
+Everything downstream is the reference's flow: reformat by tau (:513-516), C(t) (:527-531),
 reshape (:535-536), PAF rotation (:567), average vector (:579-583), spherical histogram (:585-630), S2 (:638-646),
 written to the same files in the same formats.
 """
@@ -25,7 +31,8 @@ def build_parser():
                                 'and conduct calculations on it, such as S^2, C(t), and others analyses.',
                                 formatter_class=argparse.ArgumentDefaultsHelpFormatter)
     p.add_argument('-s', type=str, dest='topfn', required=False, nargs='+', default=[],
-                   help='Topology file(s); accepted for command-line compatibility, not read on this path.')
+                   help='Reference structure(s) for the superposition of coordinate inputs (.npy / .npz); ignored '
+                        'for X-H vector inputs.')
     p.add_argument('-f', '--infn', type=str, dest='infn', required=True, nargs='+',
                    help='One or more X-H vector trajectories (.npy / .npz). Multiple trajectories are analysed '
                         'separately in C(t)-calculations, but otherwise aggregated.')
@@ -57,13 +64,44 @@ def build_parser():
     return p
 
 
-def _load(fn):
+def _load_reference(fn):
+    ref = np.load(fn, allow_pickle=True)
+    if not isinstance(ref, np.ndarray):
+        ref = ref['xyz']
+    ref = np.asarray(ref, dtype=np.float32)
+    return ref[0] if ref.ndim == 3 else ref
+
+
+def _from_coordinates(z, ref_fn):
+    """obtain_XHvecs before and after centre + superpose (:461-469) for one coordinate trajectory."""
+    import torch
+    from . import traj
+    xyz = np.ascontiguousarray(z['xyz'], dtype=np.float32)
+    index_h, index_x = np.asarray(z['indexH']), np.asarray(z['indexX'])
+    if len(index_h) == 0 or len(index_h) != len(index_x):
+        print("= = = ERROR: selection text failed to find atoms!", file=sys.stderr)
+        sys.exit(1)
+    fit = np.asarray(z['fit']) if 'fit' in z else np.arange(xyz.shape[1])
+    ref = _load_reference(ref_fn) if ref_fn else xyz[0]
+    print("= = = File loaded - it has %i atoms and %i frames." % (xyz.shape[1], xyz.shape[0]))
+    xd = torch.from_numpy(xyz).cuda()
+    unfit = traj.xh_vectors_device(xd, index_h, index_x).cpu().numpy()
+    fitv = traj.xh_vectors_superposed_device(xd, ref, fit, index_h, index_x).cpu().numpy()
+    print("= = = Molecule centered and fitted.")
+    return fitv, unfit
+
+
+def _load(fn, ref_fn=None):
     if fn.endswith('.npy'):
         return np.load(fn), None, None, None
     if fn.endswith('.npz'):
         z = np.load(fn, allow_pickle=True)
-        return (z['vecs'], z['vecs_unfitted'] if 'vecs_unfitted' in z else None,
-                list(z['names']) if 'names' in z else None, float(z['dt']) if 'dt' in z else None)
+        names = list(z['names']) if 'names' in z else None
+        dt = float(z['dt']) if 'dt' in z else None
+        if 'xyz' in z:
+            fitv, unfit = _from_coordinates(z, ref_fn)
+            return fitv, unfit, names, dt
+        return z['vecs'], z['vecs_unfitted'] if 'vecs_unfitted' in z else None, names, dt
     print("= = = ERROR: %s: only .npy/.npz X-H vector trajectories are accepted on this path "
           "(trajectory reading via mdtraj is out of scope)." % fn, file=sys.stderr)
     sys.exit(2)
@@ -87,8 +125,16 @@ def main(argv=None):
             sys.exit(23)
 
     vecXH, vecXHfit, resXH, deltaT = [], [], None, args.dt
-    for fn in args.infn:
-        fit, unfit, names, dt = _load(fn)
+    n_refs = len(args.topfn)
+    if n_refs > 1 and n_refs != len(args.infn):
+        print("= = ERROR: When giving multiple reference files, you must have one for each trajecfile file given!",
+              file=sys.stderr)                                            # :411-414
+        sys.exit(1)
+    for i_fn, fn in enumerate(args.infn):
+        ref_fn = None
+        if n_refs and args.topfn[0].endswith(('.npy', '.npz')):
+            ref_fn = args.topfn[i_fn] if n_refs > 1 else args.topfn[0]
+        fit, unfit, names, dt = _load(fn, ref_fn)
         fit = np.asarray(fit, dtype=np.float32)
         if fit.ndim != 3 or fit.shape[-1] != 3:
             print("= = = ERROR: %s does not hold a (frames, bonds, 3) array." % fn, file=sys.stderr)

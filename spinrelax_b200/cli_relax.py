@@ -1,10 +1,13 @@
-"""CLI mirror of calculate-relaxations-multi-field.py for the prediction mode (no `--opt`):
+"""CLI mirror of calculate-relaxations-multi-field.py: prediction and optimisation against experiment.
 
     python -m spinrelax_b200.cli_relax -f rotdif_fittedCt.dat --distfn rotdif_vecHistogram.npz \
-           -D "Diso" --aniso a [--zeta z] [--csa v|file] -o rotdif expt1.dat expt2.dat ...
+           -D "Diso" --aniso a [--zeta z] [--csa v|file] [--opt Diso,rsCSA --cycles 10 --tol 1e-6] \
+           -o rotdif expt1.dat expt2.dat ...
 
 Flags follow the reference (:41-105).  Output: `<o>_<A><B>_<MHz>MHz_<Type>.xvg` per experiment file
-(spectral_densities.py:775-780, :1178-1194).  All J(omega) / R1 / R2 / NOE arithmetic runs on the GPU.
+(spectral_densities.py:775-780, :1178-1194) and, after a residue-specific CSA optimisation, `<o>_CSA_opt.dat`
+(:219-225).  All J(omega) / R1 / R2 / NOE arithmetic runs on the GPU; `--localopt powell` replays the reference's
+residue-by-residue Powell searches instead of the batched solver.
 """
 import argparse
 import sys
@@ -35,9 +38,16 @@ def build_parser():
     p.add_argument('--zeta', type=float, default=0.890023, help='Zero-point vibration scaling of the C(t) magnitudes.')
     p.add_argument('--csa', type=str, default=None, help='Average CSA value, or a file with `residue CSA` lines.')
     p.add_argument('--opt', '--fit', type=str, dest='listOptParams', default=None,
-                   help='Parameter optimisation against experiment: not part of this path.')
-    p.add_argument('--cycles', type=int, default=10, help='Accepted, unused.')
-    p.add_argument('--tol', type=float, default=1e-6, help='Accepted, unused.')
+                   help='Perform optimisation against all given experimental data, over the following possible '
+                        'parameters %s (comma-separated, in the order used in the optimisation loop).'
+                        % sd.spinRelaxationExperiments.listAllowedOptimisationVariables)
+    p.add_argument('--cycles', type=int, default=10,
+                   help='Maximum number of global/local refinement cycles when both are optimised.')
+    p.add_argument('--tol', type=float, default=1e-6,
+                   help='Tolerance for terminating the global/local cycles early, as a fractional change.')
+    p.add_argument('--localopt', type=str, default='batched', choices=['batched', 'powell'],
+                   help='Residue-specific CSA solver: all residues at once on the GPU, or the reference\'s '
+                        'residue-by-residue Powell.')
     return p
 
 
@@ -65,9 +75,6 @@ def parse_rotdif_params(D=None, tau=None, aniso=None):
 def main(argv=None):
     time_start = time.time()
     args = build_parser().parse_args(argv)
-    if args.listOptParams is not None:
-        print("= = = ERROR: --opt (Powell optimisation against experiment) is not part of this path.", file=sys.stderr)
-        sys.exit(2)
     models = fitct.read_fittedCt_parameters(args.in_Ct_fn)
     if models.nModels == 0:
         print("= = = ERROR: The fitted-Ct file %s was read, but did not yield any usable parameters!" % args.in_Ct_fn)
@@ -80,12 +87,14 @@ def main(argv=None):
     elif args.refPDBFile is not None:
         print("= = = ERROR: --refpdb needs mdtraj, which is outside this path; use --distfn.", file=sys.stderr)
         sys.exit(2)
-    ex = sd.spinRelaxationExperiments(rot, models)
+    ex = sd.spinRelaxationExperiments(rot, models, local_mode=args.localopt)
     for f in args.expFiles:
         ex.add_experiment(f)
     if args.zeta != 1.0:
         print(" = = Applying scaling of all C(t) magnitudes to account for zero-point QM vibrations (zeta) of %g" % args.zeta)
         ex.set_global_zeta(args.zeta)
+    ex.map_experiment_peaknames_to_models()
+    ex.report_maps()
     if args.csa is None:
         print("= = = Using default CSA value respective to each experiment.")
     else:
@@ -104,8 +113,23 @@ def main(argv=None):
             if np.fabs(v) > 1.0:
                 v *= 1e-6
             ex.initialise_CSA_array(models.get_names(), np.repeat(v, models.nModels))
-    ex.eval_all(bVerbose=True)
-    ex.export_xvg(args.out_pref, bIncludeExpt=False)
+    if args.listOptParams is None:
+        ex.eval_all(bVerbose=True)
+        ex.export_xvg(args.out_pref, bIncludeExpt=False)
+        print("= = Finished. Total seconds elapsed: %g" % (time.time() - time_start))
+        return
+    ex.parse_optimisation_params(args.listOptParams.split(','))
+    print("= = = Parsed optimiser input %s." % args.listOptParams)
+    print("    ... conducting global optimisations over parameters %s ..." % (ex.listUpdateVariables))
+    if ex.bDoLocalOpt:
+        print("    ... conducting local optimisations over residue-specific CSA...")
+    chisq = ex.perform_optimisation(maxCycles=args.cycles, tol=args.tol)
+    print("= = = Optimisation complete. Final chi-value: %g" % np.sqrt(chisq))
+    ex.export_xvg(args.out_pref, bIncludeExpt=True)
+    if ex.bDoLocalOpt and ex.bOptCompleted:
+        with open(args.out_pref + '_CSA_opt.dat', 'w') as fp:
+            for x, y in zip(ex.localCtModels.get_names(), ex.get_first_csa()):
+                print("%s %g" % (x, y), file=fp)
     print("= = Finished. Total seconds elapsed: %g" % (time.time() - time_start))
 
 

@@ -481,6 +481,19 @@ class spinRelaxationBase:
         self.update_values(v, e, ind=ind)
         return v
 
+    def calc_chisq(self, Target, dTarget=None, indices=None):
+        """(:803-818) mean squared deviation weighted by experimental and predicted variances."""
+        v, e = self.values, self.errors
+        if indices is not None:
+            v = v[indices]
+            if e is not None:
+                e = e[indices]
+        if e is not None and dTarget is not None:
+            return np.mean(np.square(v - Target) / (np.square(dTarget) + np.square(e)))
+        if e is None:
+            return np.mean(np.square(v - Target) / np.square(dTarget))
+        return np.mean(np.square(v - Target) / np.square(e))
+
     def get_suffix_from_conditions(self):
         return '_%s%s_%iMHz_%s' % (self.angFreq.gA.isotope, self.angFreq.gB.isotope,
                                    round(self.angFreq.get_magnetic_field(unit='MHz')), self.name)
@@ -519,18 +532,41 @@ class spinRelaxationNOE(spinRelaxationBase):
     _col = 2
 
 
+def _BAIL(functionName, message):
+    print("= = ERROR in function %s : %s" % (functionName, message), file=sys.stderr)
+    sys.exit(1)
+
+
 class spinRelaxationExperiments:
     """Container for several experiments sharing one tumbling model and one set of C(t) models
-    (spectral_densities.py:909-1420).  Reproduced: add_experiment (:935-1010), set_global_zeta, eval_all (:1145-1150),
-    initialise_CSA_array, export_xvg (:1178-1194).  The Powell optimisers over Diso / Daniso / zeta / CSA / rsCSA
-    (:1302-1447) are not part of this path; the CSA grids they generate are served by `relax_grid`."""
+    (spectral_densities.py:909-1420): add_experiment (:935-1010), the peak-name maps (:1050-1097), eval_all (:1145-1150),
+    initialise_CSA_array, export_xvg (:1178-1194) and the optimisation against experiment over Diso / Daniso / zeta /
+    CSA / rsCSA (:1196-1447).  Global steps are SciPy's Powell on the host exactly as in the reference, every function
+    evaluation being one batched GPU evaluation of all residues; the residue-specific CSA step is solved for all
+    residues at once (`local_mode='batched'`: vectorised bracketing + golden section, one GPU launch per experiment and
+    iteration) or, for step-by-step parity with the reference, residue by residue with Powell (`local_mode='powell'`)."""
 
-    def __init__(self, globalRotDif=None, localCtModels=None):
+    listAllowedOptimisationVariables = ['Diso', 'Daniso', 'CSA', 'zeta', 'rsCSA']
+    dictStepSizes = {'Diso': 1e-5, 'Daniso': 0.1, 'zeta': 0.1, 'CSA': 1e-5, 'rsCSA': 1e-5}
+    dictExportScaling = {'Diso': 1.0, 'Daniso': 1.0, 'zeta': 1.0, 'CSA': 1e6, 'rsCSA': 1e6}
+    dictExportUnits = {'Diso': 'ps^-1', 'Daniso': 'a.u.', 'zeta': 'a.u.', 'CSA': 'ppm', 'rsCSA': 'ppm'}
+
+    def __init__(self, globalRotDif=None, localCtModels=None, local_mode='batched'):
         self.numExpts = 0
         self.spinrelax = []
         self.data = []
         self.globalRotDif = globalRotDif
         self.localCtModels = localCtModels
+        self.mapModelNames = []
+        self.mapExptCoverage = []
+        self.bOptInitialised = False
+        self.bOptCompleted = False
+        self.bDoLocalOpt = False
+        self.listUpdateVariables = []
+        self.chisq = None
+        self.local_mode = local_mode
+        self.bVerboseOpt = True
+        self.bAliasQuirk = True
 
     def add_experiment(self, fileName, bIgnoreErrors=False):
         strType = nucleiA = nucleiB = freq = None
@@ -580,14 +616,79 @@ class spinRelaxationExperiments:
         self.data.append(dict(names=np.array(names), y=np.array(values, dtype=float), dy=errors))
         self.numExpts += 1
 
+    # ---- peak-name maps (:1050-1097) -------------------------------------------------------------------
+    def map_experiment_peaknames_to_models(self):
+        if self.localCtModels is None:
+            print("ERROR in spinRelaxationExperiments.map_peak_names: need a local C(t) model to map experimental "
+                  "peak names!", file=sys.stderr)
+            sys.exit(1)
+        namesCt = np.array([str(x) for x in self.localCtModels.get_names()])
+        if self.globalRotDif is not None and getattr(self.globalRotDif, 'bVecs', False):
+            namesRotdif = [str(x) for x in self.globalRotDif.get_names()]
+            if list(namesCt) != namesRotdif:
+                print("ERROR in spinRelaxationExperiments.map_peak_names: local C(t) model and global "
+                      "rotational-diffusion model do not have matching peak names!", file=sys.stderr)
+                sys.exit(1)
+        print("    ....mapping peak sets (residue IDs) between simulated localCtModels and expeirmental datasets")
+        self.mapModelNames = []
+        for i in range(self.numExpts):        # gm.list_get_map(namesCt, data names): model index of every peak found
+            tmp = []
+            for x in self.data[i]['names']:
+                t = np.where(namesCt == x)[0]
+                if len(t) > 0:
+                    tmp.append(t[0])
+            self.mapModelNames.append(tmp)
+        self.mapExptCoverage = []
+        for i in range(self.localCtModels.nModels):
+            l = []
+            for exptID in range(self.numExpts):
+                ret = np.where(self.data[exptID]['names'] == namesCt[i])[0]
+                if len(ret) > 0:
+                    l.append((exptID, ret[0]))
+            self.mapExptCoverage.append(l)
+
+    def report_maps(self):
+        print("Number of simulation residues covered by each experiment:",
+              ''.join(' %i' % len(x) for x in self.mapModelNames))
+        print("Number of Experiments covering each simulation residue:",
+              ''.join(' %i' % len(x) for x in self.mapExptCoverage))
+
+    # ---- parameter access (:1196-1210, :1244-1266) ----------------------------------------------------
+    def set_global_Diso(self, Diso):
+        self.globalRotDif.set_Diso(Diso)
+
+    def get_global_Diso(self):
+        return self.globalRotDif.get_Diso()
+
+    def set_global_Daniso(self, Daniso):
+        self.globalRotDif.set_Daniso(Daniso)
+
+    def get_global_Daniso(self):
+        return self.globalRotDif.get_Daniso()
+
     def set_global_zeta(self, zeta):
         self.localCtModels.set_zeta(zeta)
+
+    def get_global_zeta(self):
+        return self.localCtModels.get_zeta()
 
     def get_zeta(self):
         return self.localCtModels.get_zeta()
 
-    def get_first_csa(self):
-        return self.spinrelax[0].angFreq.gA.csa
+    def set_all_csa(self, csa, ind=None):
+        for sp in self.spinrelax:
+            sp.angFreq.gA.set_csa(csa, ind)
+
+    def get_first_csa(self, ind=None):
+        return self.spinrelax[0].angFreq.gA.get_csa(ind)
+
+    def return_get_function(self, param):
+        return {'Diso': self.get_global_Diso, 'Daniso': self.get_global_Daniso, 'zeta': self.get_global_zeta,
+                'CSA': self.get_first_csa}.get(param)
+
+    def return_set_function(self, param):
+        return {'Diso': self.set_global_Diso, 'Daniso': self.set_global_Daniso, 'zeta': self.set_global_zeta,
+                'CSA': self.set_all_csa}.get(param)
 
     def initialise_CSA_array(self, namesCSA, CSAValues):
         namesCSA = [str(x) for x in namesCSA]
@@ -610,16 +711,201 @@ class spinRelaxationExperiments:
             out.append([v, e] if e is not None else [v])
         return out
 
+    # ---- optimisation against experiment (:1268-1447) --------------------------------------------------
+    def parse_optimisation_params(self, listOpts):
+        self.bOptInitialised = False
+        self.bDoLocalOpt = False
+        self.listUpdateVariables, self.listStepSizes, self.listSetFunctions, self.listGetFunctions = [], [], [], []
+        if 'CSA' in listOpts and 'rsCSA' in listOpts:
+            _BAIL("parse_optimisation_params", "Cannot run both global CSA as well as residue-specific CSA optimisation!")
+        for o in listOpts:
+            if o not in spinRelaxationExperiments.listAllowedOptimisationVariables:
+                _BAIL("parse_optimisation_params", "Optimisation variable %s not found in list!\nPossibilities are: %s "
+                      % (o, spinRelaxationExperiments.listAllowedOptimisationVariables))
+            if o == 'rsCSA':
+                csa = self.get_first_csa()
+                if not type(csa) is np.ndarray:
+                    print("    ... NOTE: CSA values have not been preset but residue-specific CSA optimisation is being "
+                          "performed. Reinitialising CSA variables as being residue-specific.")
+                    self.initialise_CSA_array(self.localCtModels.get_names(), np.repeat(csa, self.localCtModels.nModels))
+                self.bDoLocalOpt = True          # does not trigger global optimisation procedures
+                continue
+            self.listGetFunctions.append(self.return_get_function(o))
+            self.listSetFunctions.append(self.return_set_function(o))
+            self.listStepSizes.append(spinRelaxationExperiments.dictStepSizes[o])
+            self.listUpdateVariables.append(o)
+        self.bOptInitialised = True
+
+    def perform_optimisation(self, maxCycles=10, tol=1e-6):
+        """(:1302-1358) global Powell rounds, residue-specific CSA rounds, or alternating cycles of both."""
+        if not self.bOptInitialised:
+            _BAIL("perform_fit", "You must first run parse_optimisation_params to tell the script what to optimise.")
+        if len(self.mapExptCoverage) == 0:
+            self.map_experiment_peaknames_to_models()
+        bDoGlobalOpt = len(self.optimisation_loop_get_globals()) > 0
+        if bDoGlobalOpt and not self.bDoLocalOpt:
+            self.optimisation_loop_do_global_step()
+            self.bOptCompleted = True
+            return self.chisq
+        if self.bDoLocalOpt and not type(self.get_first_csa()) is np.ndarray:
+            _BAIL("perform_optimisation", "CSA values are not an array for local optimisation!")
+        if self.bDoLocalOpt and not bDoGlobalOpt:
+            self.eval_all()
+            self.optimisation_loop_do_local_step()
+            self.bOptCompleted = True
+            self.chisq = self.calc_chisq()
+            return self.chisq
+        if bDoGlobalOpt and self.bDoLocalOpt:
+            bFirst = True
+            for n in range(maxCycles):
+                paramPrev = self.optimisation_loop_get_globals()
+                self.optimisation_loop_do_global_step()
+                paramNow = self.optimisation_loop_get_globals()
+                if not bFirst and np.allclose(paramPrev, paramNow, rtol=tol):
+                    self.bOptCompleted = True
+                    break
+                csaPrev = np.array(self.get_first_csa())
+                self.optimisation_loop_do_local_step()
+                csaNow = self.get_first_csa()
+                # The reference's csaPrev is an alias of the array its local step updates in place (:1341-1344), so
+                # its convergence test always passes from the second cycle on; bAliasQuirk reproduces that.
+                if not bFirst and (self.bAliasQuirk or np.allclose(csaPrev, csaNow, rtol=tol)):
+                    self.chisq = self.calc_chisq()
+                    self.bOptCompleted = True
+                    break
+                bFirst = False
+            return self.chisq
+        _BAIL("perform_optimisation", "neither global or local optimisation have been successfully specified!")
+
+    def optimisation_loop_do_global_step(self):
+        from scipy.optimize import fmin_powell
+        fminOut = fmin_powell(optimisation_loop_inner_function, x0=self.optimisation_loop_get_globals(),
+                              direc=self.optimisation_loop_get_direc(), args=(self, '1'), full_output=True,
+                              disp=self.bVerboseOpt)
+        if self.bVerboseOpt:
+            print("= = = Optimisation complete over variables: %s" % self.optimisation_loop_get_param_names())
+            print(fminOut)
+        self.chisq = fminOut[1]
+
+    def optimisation_loop_do_local_step(self):
+        """Residue-specific CSA (:1371-1384)."""
+        if self.local_mode == 'powell':
+            from scipy.optimize import fmin_powell
+            for i in range(self.localCtModels.nModels):
+                if len(self.mapExptCoverage[i]) > 0:
+                    fmin_powell(optimisation_loop_rsCSA_inner_function, x0=self.get_first_csa(ind=i),
+                                direc=[spinRelaxationExperiments.dictStepSizes['rsCSA']],
+                                args=(self, i, self.mapExptCoverage[i]), full_output=False, disp=self.bVerboseOpt)
+            return
+        self._local_step_batched()
+
+    def _rsCSA_objective(self, csa):
+        """optimisation_loop_rsCSA_inner_function (:1430-1447) for ALL residues at once: chi^2_i of residue i at csa_i."""
+        self.set_all_csa(np.array(csa))
+        self.eval_all()
+        n = self.localCtModels.nModels
+        chi, cnt = np.zeros(n), np.zeros(n)
+        for i, cover in enumerate(self.mapExptCoverage):
+            for exptID, peakID in cover:
+                sp, target = self.spinrelax[exptID], self.data[exptID]
+                dv = sp.errors[i] if sp.errors is not None else 0.0
+                dt = target['dy'][peakID] if target['dy'] is not None else 0.0
+                w = dv ** 2 + dt ** 2
+                chi[i] += (sp.values[i] - target['y'][peakID]) ** 2 / (w if w != 0 else 1.0)
+                cnt[i] += 1
+        return chi / np.maximum(cnt, 1)
+
+    def _local_step_batched(self, nGolden=48):
+        """All residue-specific 1-D minimisations at once: downhill bracketing from the current CSA with the
+        reference's step size, then golden-section refinement (bracket shrinks by 0.618^48 ~ 1e-10)."""
+        x0 = np.array(self.get_first_csa(), dtype=float)
+        active = np.array([len(c) > 0 for c in self.mapExptCoverage])
+        before = [(sp.values.copy(), None if sp.errors is None else sp.errors.copy()) for sp in self.spinrelax]
+        gold = 1.618033988749895
+        step = spinRelaxationExperiments.dictStepSizes['rsCSA']
+        xa, xb = x0.copy(), x0 + step
+        fa, fb = self._rsCSA_objective(xa), self._rsCSA_objective(xb)
+        swap = fb > fa
+        xa[swap], xb[swap] = xb[swap], xa[swap].copy()
+        fa[swap], fb[swap] = fb[swap], fa[swap].copy()
+        xc = xb + gold * (xb - xa)
+        fc = self._rsCSA_objective(xc)
+        for _ in range(40):
+            grow = active & (fc < fb)
+            if not grow.any():
+                break
+            xa[grow], fa[grow] = xb[grow], fb[grow]
+            xb[grow], fb[grow] = xc[grow], fc[grow]
+            xc = np.where(grow, xb + gold * (xb - xa), xc)
+            fnew = self._rsCSA_objective(np.where(grow, xc, xb))
+            fc = np.where(grow, fnew, fc)
+        lo, hi = np.minimum(xa, xc), np.maximum(xa, xc)
+        r = 1.0 / gold
+        x1, x2 = hi - r * (hi - lo), lo + r * (hi - lo)
+        f1, f2 = self._rsCSA_objective(x1), self._rsCSA_objective(x2)
+        for _ in range(nGolden):
+            left = f1 < f2
+            hi = np.where(left, x2, hi)
+            lo = np.where(left, lo, x1)
+            x2n = np.where(left, x1, lo + r * (hi - lo))
+            x1n = np.where(left, hi - r * (hi - lo), x2)
+            fnew = self._rsCSA_objective(np.where(left, x1n, x2n))
+            f2n = np.where(left, f1, fnew)
+            f1n = np.where(left, fnew, f2)
+            x1, x2, f1, f2 = x1n, x2n, f1n, f2n
+        best = np.where(f1 < f2, x1, x2)
+        self.set_all_csa(np.where(active, best, x0))
+        self.eval_all()
+        # The reference's residue loop only re-evaluates the (experiment, residue) pairs that have a measured peak
+        # (:1375-1384); predictions of unresolved peaks keep the value they had before the local step.
+        covered = [set() for _ in self.spinrelax]
+        for i, cover in enumerate(self.mapExptCoverage):
+            for exptID, _ in cover:
+                covered[exptID].add(i)
+        for e, sp in enumerate(self.spinrelax):
+            stale = [i for i in range(self.localCtModels.nModels) if i not in covered[e]]
+            if stale:
+                sp.values[stale] = before[e][0][stale]
+                if sp.errors is not None and before[e][1] is not None:
+                    sp.errors[stale] = before[e][1][stale]
+
+    def optimisation_loop_get_param_names(self):
+        return self.listUpdateVariables
+
+    def optimisation_loop_get_direc(self):
+        n = len(self.listStepSizes)
+        out = np.zeros((n, n))
+        for i in range(n):
+            out[i, i] = self.listStepSizes[i]
+        return out
+
+    def optimisation_loop_get_globals(self):
+        return [func() for func in self.listGetFunctions]
+
+    def optimisation_loop_set_globals(self, vNew):
+        for func, v in zip(self.listSetFunctions, vNew):
+            func(v)
+
+    def calc_chisq(self):
+        chisq = 0.0
+        for i, sp in enumerate(self.spinrelax):
+            chisq += sp.calc_chisq(self.data[i]['y'], self.data[i]['dy'], self.mapModelNames[i])
+        return chisq / self.numExpts
+
     def print_parameters(self, style='stdout', fp=sys.stdout):
-        """`# Fixed <name>: <value> <unit>` lines of the .xvg header (:1224-1242; nothing is optimised here)."""
-        csa = self.get_first_csa()
-        rows = (('Diso', self.globalRotDif.get_Diso(), 'ps^-1', 'Fixed'),
-                ('Daniso', self.globalRotDif.get_Daniso(), 'a.u.', 'Fixed'),
-                ('CSA', (np.mean(csa) if isinstance(csa, np.ndarray) else csa) * 1e6, 'ppm',
-                 'FixedMean' if isinstance(csa, np.ndarray) else 'Fixed'),
-                ('zeta', self.get_zeta(), 'a.u.', 'Fixed'))
-        for name, v, unit, tag in rows:
-            print('# %s %s: %g %s' % (tag, name, v, unit), file=fp)
+        """`# Fixed|Optimised <name>: <value> <unit>` lines of the .xvg header (:1224-1242)."""
+        for x in spinRelaxationExperiments.listAllowedOptimisationVariables:
+            if x == 'rsCSA':
+                continue
+            v = self.return_get_function(x)()
+            s1 = 'Optimised' if x in self.listUpdateVariables else 'Fixed'
+            if x == 'CSA' and type(v) is np.ndarray:
+                v = np.mean(v)
+                s1 = 'OptimisedMean' if (self.bOptCompleted and self.bDoLocalOpt) else 'FixedMean'
+            print('# %s %s: %g %s' % (s1, x, v * spinRelaxationExperiments.dictExportScaling[x],
+                                      spinRelaxationExperiments.dictExportUnits[x]), file=fp)
+        if self.bOptCompleted:
+            print('# Optimised chi: %g a.u.' % np.sqrt(self.chisq), file=fp)
 
     def export_xvg(self, filePrefix, bIncludeExpt=False):
         for i, sp in enumerate(self.spinrelax):
@@ -637,3 +923,32 @@ class spinRelaxationExperiments:
                         print(("%s %g" % (d['names'][k], d['y'][k])) if d['dy'] is None
                               else ("%s %g %g" % (d['names'][k], d['y'][k], d['dy'][k])), file=fp)
                     print('&', file=fp)
+
+
+def optimisation_loop_inner_function(params, *args):
+    """(:1422-1428) objective of the global Powell step: set the globals, re-evaluate everything, chi^2."""
+    objExpts = args[0]
+    objExpts.optimisation_loop_set_globals(params)
+    objExpts.eval_all(bVerbose=False)
+    chisq = objExpts.calc_chisq()
+    if objExpts.bVerboseOpt:
+        print("    ....optimisation step. Params: %s chisq: %g" % (params, chisq))
+    return chisq
+
+
+def optimisation_loop_rsCSA_inner_function(params, *args):
+    """(:1430-1447) objective of one residue's CSA step."""
+    objExpts, ind, listCalcs = args[0], args[1], args[2]
+    objExpts.set_all_csa(params[0], ind=ind)
+    chisq = 0.0
+    for exptID, peakID in listCalcs:
+        sp, target = objExpts.spinrelax[exptID], objExpts.data[exptID]
+        v = sp.eval(ind=ind)
+        t = target['y'][peakID]
+        dv = sp.errors[ind] if sp.errors is not None else 0.0
+        dt = target['dy'][peakID] if target['dy'] is not None else 0.0
+        w = dv ** 2 + dt ** 2
+        if w == 0:
+            w = 1
+        chisq += (v - t) ** 2 / w
+    return chisq / len(listCalcs)

@@ -331,6 +331,72 @@ def golden_relax_cli():
          **{"expt_" + k: np.array(v) for k, v in expt.items()})
 
 
+def golden_relax_opt():
+    """calculate-relaxations-multi-field.py --opt ... (Powell optimisation against experiment, spectral_densities.py
+    :1302-1447) run unmodified.  The "experiments" are the reference's own predictions at perturbed parameters
+    (Diso x 1.08, residue-specific CSA), two fields, so the optimum is known to exist and is well conditioned."""
+    import subprocess
+    import tempfile
+    g = np.load(os.path.join(OUT, "relax.npz"))
+    gc = np.load(os.path.join(OUT, "relax_cli.npz"))
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([ref_loader.STUBS, ref_loader.REF_BUILD, ref_loader.REFERENCE]))
+    script = ref_loader.REFERENCE + "/calculate-relaxations-multi-field.py"
+    rng = np.random.default_rng(synth.BASE_SEED + 55)
+    csa_true = -170e-6 * (1.0 + 0.08 * rng.standard_normal(6))
+    res = {}
+    with tempfile.TemporaryDirectory() as td:
+        e = np.empty(2, dtype=object); e[0] = g["edges_phi"]; e[1] = g["edges_cos"]
+        np.savez_compressed(td + "/h_vecHistogram.npz", names=np.arange(6), dataType="LambertCylindrical", bHistogram=True,
+                            edges=e, axisLabels=["phi", "cos(theta)"], data=g["hist"].astype(float))
+        with open(td + "/x_fittedCt.dat", "w") as fp:
+            fp.write(str(gc["fitted"]))
+        with open(td + "/csa_true.dat", "w") as fp:
+            for i, c in enumerate(csa_true):
+                fp.write("%d %.9g\n" % (i, c))
+        # 1. "experimental" data = prediction at the true parameters, residues 0..5 (one peak missing in one file)
+        dummy = []
+        for f in (600.133, 800.25):
+            for t in ("R1", "R2", "NOE"):
+                fn = td + "/d_%s_%d.dat" % (t, f)
+                with open(fn, "w") as fp:
+                    fp.write("# Type %s\n# NucleiA 15N\n# NucleiB 1H\n# Frequency %g\n" % (t, f))
+                    fp.write("".join("%d 1.0 0.1\n" % i for i in range(6)))
+                dummy.append(fn)
+        cmd = [sys.executable, script, "-f", td + "/x_fittedCt.dat", "--distfn", td + "/h_vecHistogram.npz", "-D", "2.268e-5",
+               "--aniso", "1.35", "--csa", td + "/csa_true.dat", "-o", td + "/true"] + dummy
+        subprocess.run(cmd, env=env, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        expt = {}
+        files = []
+        for f in (600, 800):
+            for t in ("R1", "R2", "NOE"):
+                rows = [l.split() for l in open(td + "/true_15N1H_%dMHz_%s.xvg" % (f, t)) if l[0] not in "#@&\n"]
+                txt = "# Type %s\n# NucleiA 15N\n# NucleiB 1H\n# Frequency %s\n" % (t, "600.133" if f == 600 else "800.25")
+                for r in rows:
+                    if t == "NOE" and f == 800 and r[0] == "4":
+                        continue                          # unresolved peak: exercises the name maps
+                    y = float(r[1])
+                    txt += "%s %.6g %.3g\n" % (r[0], y, 0.02 * abs(y))
+                expt["%s_%d" % (t, f)] = txt
+                fn = td + "/e_%s_%d.dat" % (t, f)
+                with open(fn, "w") as fp:
+                    fp.write(txt)
+                files.append(fn)
+        # 2. the optimisation modes
+        for tag, opt, extra in (("Diso", "Diso", []), ("rsCSA", "rsCSA", []), ("mixed", "Diso,rsCSA", ["--cycles", "4"])):
+            cmd = [sys.executable, script, "-f", td + "/x_fittedCt.dat", "--distfn", td + "/h_vecHistogram.npz", "-D", "2.1e-5",
+                   "--aniso", "1.35", "-o", td + "/" + tag, "--opt", opt] + extra + files
+            out = subprocess.run(cmd, env=env, check=True, capture_output=True, text=True).stdout
+            chi = [l for l in out.splitlines() if "Final chi-value" in l][-1]
+            res["chi_" + tag] = np.array(float(chi.split(":")[-1]))
+            for f in (600, 800):
+                for t in ("R1", "R2", "NOE"):
+                    res["xvg_%s_%s_%d" % (tag, t, f)] = np.array(open(td + "/%s_15N1H_%dMHz_%s.xvg" % (tag, f, t)).read())
+            if "rsCSA" in opt:
+                res["csa_" + tag] = np.loadtxt(td + "/%s_CSA_opt.dat" % tag)
+            print(tag, chi)
+    save("relax_opt.npz", csa_true=csa_true, **{"expt_" + k: np.array(v) for k, v in expt.items()}, **res)
+
+
 def main():
     if not ref_loader.available():
         sys.exit("reference tree not found at %s" % ref_loader.REFERENCE)
@@ -343,6 +409,7 @@ def main():
     golden_fit()
     golden_relax()
     golden_relax_cli()
+    golden_relax_opt()
 
 
 if __name__ == "__main__":

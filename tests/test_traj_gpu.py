@@ -73,3 +73,26 @@ def test_superposition_removes_tumbling():
     drift_raw = np.abs((raw[0] * raw[-1]).sum(-1) - (internal[0] * internal[-1]).sum(-1)).max()
     drift_fit = np.abs((fitv[0] * fitv[-1]).sum(-1) - (internal[0] * internal[-1]).sum(-1)).max()
     assert drift_fit < 5e-4 < drift_raw
+
+
+def test_cli_ct_from_coordinates(tmp_path):
+    """`calculate-Ct-from-traj`-style run from Cartesian coordinates: Ctext from the raw vectors, Ctint from the
+    superposed ones, both against the oracle chain (traj_oracle -> ct_oracle)."""
+    import contextlib, io
+    from spinrelax_b200 import cli_ct, io_formats, synth
+    nF, nRes = 1200, 6
+    xyz, sel, ref = synth.backbone_trajectory(nF, nRes, seed=31)
+    ih, ix, fit = sel["name H"], sel["name N and not resname PRO"], sel["custom occupancy"]
+    np.savez(tmp_path / "trj.npz", xyz=xyz, indexH=ih, indexX=ix, fit=fit, names=np.arange(2, 2 + nRes), dt=10.0)
+    np.save(tmp_path / "ref.npy", ref)
+    pref = str(tmp_path / "out")
+    with contextlib.redirect_stdout(io.StringIO()):
+        cli_ct.main(["-s", str(tmp_path / "ref.npy"), "-f", str(tmp_path / "trj.npz"), "--tau", "3000", "-o", pref, "--Ct"])
+    ofit, _ = traj_oracle.xh_vectors_superposed(xyz, ref, fit, ih, ix)
+    oraw = traj_oracle.xh_vectors(xyz, ih, ix)
+    for suffix, vecs in (("_Ctint.dat", ofit), ("_Ctext.dat", oraw)):
+        legs, x, y, dy = io_formats.load_sxydylist(pref + suffix)
+        v4 = ct_oracle.reformat_by_tau([vecs], 10.0, 3000.0)
+        oCt, odCt = ct_oracle.ct_palmer(v4.astype(np.float64))
+        assert legs == [str(i) for i in range(2, 2 + nRes)]
+        assert rel_err(y, oCt.T) < 5e-6 and np.max(np.abs(dy - odCt.T)) < 2e-6
