@@ -156,8 +156,22 @@ int sr_rotate_vectors_f32_f64(const float* d_v, long long n, const double* h_q, 
 int sr_dq_moments(const float* d_q, long long N, const long long* d_lags, int nLags, long long min_lag, int nCh,
                   double* d_M, void* stream);
 
+/* The same for replica `replica` of `nReplicas` equally long trajectories whose displacement samples are pooled
+ * (calculate-dq-distribution-multi.py:529-540): sub-chunk boundaries are taken on the pooled sample index, and
+ * with accumulate != 0 the sums are added to d_M so that one call per replica (or one all-reduce over ranks that
+ * each hold one replica) yields the pooled moments. */
+int sr_dq_moments_pooled(const float* d_q, long long N, const long long* d_lags, int nLags, long long min_lag, int nCh,
+                         int replica, int nReplicas, int accumulate, double* d_M, void* stream);
+
 /* obtain_self_dq(q, delta): d_out (N-delta, 4) float64, imaged so that w >= 0 (quat_reduce_simd). */
 int sr_dq_self(const float* d_q, long long N, long long delta, double* d_out, void* stream);
+
+/* 3-D histogram of the vector part of dq(t) for one lag over the cube spanned by d_edges (nb + 1 float64 edges,
+ * the same on all three axes: np.linspace(-1, 1, nb + 1)), the --hist option of calculate-dq-distribution.py:633-647
+ * (np.histogramdd semantics).  Counts are ADDED into d_counts [nb][nb][nb]; samples within 4 ulp of an edge are
+ * not counted but listed in d_amb_idx (frame index t) for the caller to bin with NumPy. */
+int sr_dq_hist3d(const float* d_q, long long N, long long delta, const double* d_edges, int nb, unsigned int* d_counts,
+                 long long* d_amb_idx, int amb_capacity, int* d_amb_count, void* stream);
 
 /* second moments of a float64 (n,3) vector list in nCh consecutive blocks: d_M [nCh][6]. */
 int sr_vec_second_moments(const double* d_v, long long n, int nCh, double* d_M, void* stream);

@@ -206,3 +206,14 @@ def anisotropies(D):
         return 3 * (d[1] - d[0]) / (2 * d[2] - d[1] - d[0])
 
     return np.mean(D), ani(D), rho(D), ani(D[::-1]), rho(D[::-1])
+
+
+def pooled_vectors(q_replicas, delta):
+    """calculate-dq-distribution-multi.py:533-539: the displacement vectors of every replica, concatenated."""
+    return np.concatenate([self_dq(q, delta)[..., 1:4] for q in q_replicas], axis=0)
+
+
+def dq_histogram3d(q, delta, nbins=101):
+    """calculate-dq-distribution.py:527-528, 633-634 (`normed=True` is NumPy < 1.24's spelling of density)."""
+    v = self_dq(q, delta)[..., 1:4]
+    return np.histogramdd(v, range=[(-1, 1)] * 3, bins=(nbins,) * 3, density=True)

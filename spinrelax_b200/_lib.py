@@ -43,7 +43,9 @@ def _declare(lib):
                               vp, vp, vp, vp, vp, vp, vp, vp, vp]),
         "sr_ct_fit_lm": (i, [vp, vp, vp, i, ll, i, vp, vp, vp, i, _c.c_double, vp, vp, vp, vp, vp]),
         "sr_dq_moments": (i, [vp, ll, vp, i, ll, i, vp, vp]),
+        "sr_dq_moments_pooled": (i, [vp, ll, vp, i, ll, i, i, i, i, vp, vp]),
         "sr_dq_self": (i, [vp, ll, ll, vp, vp]),
+        "sr_dq_hist3d": (i, [vp, ll, ll, vp, i, vp, vp, i, vp, vp]),
         "sr_vec_second_moments": (i, [vp, ll, i, vp, vp]),
         "sr_sphere_hist": (i, [vp, ll, i, dp, i, i, vp, _c.c_double, _c.c_double, vp, vp, i, vp, vp]),
         "sr_xh_vectors": (i, [vp, ll, i, vp, vp, i, vp, vp]),

@@ -38,7 +38,7 @@ __device__ __forceinline__ Vec3d dq_vector(const float4 a, const float4 b) {
 // FP64 instructions, 16 bytes of L1/L2 traffic.  grid.x = lagTile * tilesMax + frameTile.
 __global__ void __launch_bounds__(kDqThreads)
 dq_moments_kernel(const float4* __restrict__ q, long long N, const long long* __restrict__ lags, int nLags, int nCh,
-                  int tilesMax, double* __restrict__ M) {
+                  int tilesMax, int replica, int nRep, double* __restrict__ M) {
   // left quaternions of the frame tile as four planes of doubles (w | x | y | z): a half-warp reads 16
   // consecutive doubles per plane (one wavefront, broadcast to the other half-warp); an array of double4
   // would cost 8 wavefronts per LDS.128 (32-byte lane stride) and saturate the shared-memory data pipe
@@ -66,11 +66,15 @@ dq_moments_kernel(const float4* __restrict__ q, long long N, const long long* __
   const long long n = N - delta;
   if (lo >= n) return;
   const long long hi = min(n, lo + kDqFrameTile);
-  const long long nb = (n + nCh - 1) / nCh;   // ceil(n / nchunk), calculate-dq-distribution.py:129
+  // Sub-chunks are consecutive blocks of ceil(n_pooled / nchunk) samples of the POOLED sample list
+  // (calculate-dq-distribution.py:129; with several replica trajectories the samples of replica r occupy
+  // [r n, (r + 1) n), calculate-dq-distribution-multi.py:533-539), so a block may straddle replicas.
+  const long long nb = (n * nRep + nCh - 1) / nCh;
+  const long long off = (long long)replica * n;          // pooled index of this replica's sample t = 0
   const float4* __restrict__ qb = q + delta;
 
-  for (long long k = lo / nb; k * nb < hi; ++k) {
-    const long long a0 = max(lo, k * nb), b0 = min(hi, (k + 1) * nb);
+  for (long long k = (off + lo) / nb; k * nb < off + hi; ++k) {
+    const long long a0 = max(lo, k * nb - off), b0 = min(hi, (k + 1) * nb - off);
     double s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0, s5 = 0;
     // software pipeline: the next four q(t + delta) are in flight while the current four are consumed; a zero
     // quaternion (past the end of the segment) yields v = 0 and needs no predicate
@@ -129,6 +133,49 @@ dq_self_kernel(const float4* __restrict__ q, long long N, long long delta, doubl
   *o = make_double4(w * sgn, v.x * sgn, v.y * sgn, v.z * sgn);
 }
 
+// 3-D histogram of the vector part of dq over [-1,1]^3 (the --hist option, calculate-dq-distribution.py:633-647:
+// np.histogramdd(v_dq, range=((-1,1),)*3, bins=(nb,nb,nb))).  dq is formed exactly like dq_self_kernel; the bin of
+// every component is located against the SAME float64 edge array NumPy builds (np.linspace), so counts are
+// identical to NumPy's unless a component lies within 4 ulp of an edge -- those samples (and NaNs) are listed for
+// the host instead of being counted.  Counts go straight to global memory: nb^3 bins (4 MB for nb = 101) live in L2.
+__device__ __forceinline__ int locate_bin(double x, const double* __restrict__ edges, int nb, bool& ambiguous) {
+  // np.histogramdd: searchsorted(edges, x, 'right') - 1, samples equal to the last edge go to the last bin,
+  // samples outside [edges[0], edges[nb]] are dropped (-1)
+  if (!(x >= edges[0] && x <= edges[nb])) { ambiguous = ambiguous || (x != x); return -1; }
+  int c = (int)floor((x - edges[0]) / (edges[nb] - edges[0]) * nb);
+  c = max(0, min(nb - 1, c));
+  while (c > 0 && x < edges[c]) --c;
+  while (c < nb - 1 && x >= edges[c + 1]) ++c;
+  const double tol = 4.0 * 2.220446049250313e-16 * fmax(fabs(x), 1e-3);
+  if (fabs(x - edges[c]) <= tol || fabs(x - edges[c + 1]) <= tol) ambiguous = true;
+  return c;
+}
+
+__global__ void __launch_bounds__(256)
+dq_hist3d_kernel(const float4* __restrict__ q, long long N, long long delta, const double* __restrict__ edges, int nb,
+                 unsigned int* __restrict__ counts, long long* __restrict__ amb_idx, int amb_capacity,
+                 int* __restrict__ amb_count) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= N - delta) return;
+  const float4 a = __ldg(q + t), b = __ldg(q + t + delta);
+  const double w1 = a.x, x1 = a.y, y1 = a.z, z1 = a.w;
+  const double w2 = b.x, x2 = b.y, y2 = b.z, z2 = b.w;
+  const double w = w1 * w2 - ((-x1) * x2 + (-y1) * y2 + (-z1) * z2);
+  const Vec3d v = dq_vector(a, b);
+  const double sgn = (w < 0.0) ? -1.0 : 1.0;
+  bool amb = false;
+  const int i = locate_bin(v.x * sgn, edges, nb, amb);
+  const int j = locate_bin(v.y * sgn, edges, nb, amb);
+  const int k = locate_bin(v.z * sgn, edges, nb, amb);
+  if (amb) {
+    const int slot = atomicAdd(amb_count, 1);
+    if (slot < amb_capacity) amb_idx[slot] = t;
+    return;
+  }
+  if (i < 0 || j < 0 || k < 0) return;
+  atomicAdd(&counts[((long long)i * nb + j) * nb + k], 1u);
+}
+
 // second moments of an arbitrary (n,3) float64 vector list, split in nCh consecutive blocks of ceil(n/nCh)
 __global__ void __launch_bounds__(kDqThreads)
 vec_moments_kernel(const double* __restrict__ v, long long n, int nCh, double* __restrict__ M) {
@@ -165,22 +212,29 @@ vec_moments_kernel(const double* __restrict__ v, long long n, int nCh, double* _
 
 }  // namespace
 
-extern "C" int sr_dq_moments(const float* d_q, long long N, const long long* d_lags, int nLags, long long min_lag,
-                             int nCh, double* d_M, void* stream) {
+extern "C" int sr_dq_moments_pooled(const float* d_q, long long N, const long long* d_lags, int nLags, long long min_lag,
+                                    int nCh, int replica, int nReplicas, int accumulate, double* d_M, void* stream) {
   SR_REQUIRE(d_q && d_lags && d_M, "sr_dq_moments: null pointer");
+  SR_REQUIRE(nReplicas >= 1 && replica >= 0 && replica < nReplicas, "sr_dq_moments: replica %d outside [0, %d)", replica,
+             nReplicas);
   SR_REQUIRE(N >= 2 && nLags > 0 && nCh >= 1, "sr_dq_moments: bad shape (N=%lld nLags=%d nCh=%d)", N, nLags, nCh);
   SR_REQUIRE(min_lag >= 1 && min_lag < N, "sr_dq_moments: min_lag %lld outside [1, N)", min_lag);
   const long long tilesMax = (N - min_lag + kDqFrameTile - 1) / kDqFrameTile;
   const long long lagTiles = (nLags + kDqLagTile - 1) / kDqLagTile;
   const long long blocks = tilesMax * lagTiles;
   SR_REQUIRE(blocks < (1LL << 31), "sr_dq_moments: %lld blocks exceed the grid limit; split the lag list", blocks);
-  SR_CUDA(cudaMemsetAsync(d_M, 0, sizeof(double) * 6 * (size_t)nLags * nCh, (cudaStream_t)stream));
+  if (!accumulate) SR_CUDA(cudaMemsetAsync(d_M, 0, sizeof(double) * 6 * (size_t)nLags * nCh, (cudaStream_t)stream));
   const int smem = (kDqFrameTile + 16 * kDqU) * (int)sizeof(double4);
   SR_CUDA(cudaFuncSetAttribute(dq_moments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   dq_moments_kernel<<<(unsigned)blocks, kDqThreads, smem, (cudaStream_t)stream>>>((const float4*)d_q, N, d_lags, nLags,
-                                                                                 nCh, (int)tilesMax, d_M);
+                                                                                 nCh, (int)tilesMax, replica, nReplicas, d_M);
   SR_CUDA(cudaGetLastError());
   return SR_OK;
+}
+
+extern "C" int sr_dq_moments(const float* d_q, long long N, const long long* d_lags, int nLags, long long min_lag,
+                             int nCh, double* d_M, void* stream) {
+  return sr_dq_moments_pooled(d_q, N, d_lags, nLags, min_lag, nCh, 0, 1, 0, d_M, stream);
 }
 
 extern "C" int sr_dq_self(const float* d_q, long long N, long long delta, double* d_out, void* stream) {
@@ -198,6 +252,18 @@ extern "C" int sr_vec_second_moments(const double* d_v, long long n, int nCh, do
   SR_CUDA(cudaMemsetAsync(d_M, 0, sizeof(double) * 6 * (size_t)nCh, (cudaStream_t)stream));
   const long long blocks = (n + kDqTile - 1) / kDqTile;
   vec_moments_kernel<<<(unsigned)blocks, kDqThreads, 0, (cudaStream_t)stream>>>(d_v, n, nCh, d_M);
+  SR_CUDA(cudaGetLastError());
+  return SR_OK;
+}
+
+extern "C" int sr_dq_hist3d(const float* d_q, long long N, long long delta, const double* d_edges, int nb,
+                            unsigned int* d_counts, long long* d_amb_idx, int amb_capacity, int* d_amb_count, void* stream) {
+  SR_REQUIRE(d_q && d_edges && d_counts && d_amb_idx && d_amb_count, "sr_dq_hist3d: null pointer");
+  SR_REQUIRE(delta >= 1 && delta < N, "sr_dq_hist3d: delta %lld outside [1, N)", delta);
+  SR_REQUIRE(nb >= 1 && nb <= 1024, "sr_dq_hist3d: %d bins per axis outside [1, 1024]", nb);
+  const long long n = N - delta;
+  dq_hist3d_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const float4*)d_q, N, delta, d_edges, nb,
+                                                                                d_counts, d_amb_idx, amb_capacity, d_amb_count);
   SR_CUDA(cudaGetLastError());
   return SR_OK;
 }

@@ -28,27 +28,64 @@ def _sym3(m6):
 # ---- GPU reductions ---------------------------------------------------------------------------------
 def dq_moment_sums(q, lags, nchunk=1):
     """Raw second-moment sums of the dq vector parts: returns (M (nLags, nCh, 6) float64, n (nLags,),
-    counts (nLags, nCh)).  q: (N, 4) float32 (w,x,y,z); lags: frame lags."""
+    counts (nLags, nCh)).  q: (N, 4) float32 (w,x,y,z) -- or (nReplicas, N, 4) / a list of equally long
+    trajectories whose displacement samples are pooled the way calculate-dq-distribution-multi.py:529-540 does
+    (sub-chunks are then blocks of the pooled sample list); lags: frame lags."""
     torch = _lib.require_cuda()
     lib = _lib.load()
     q32 = np.ascontiguousarray(q, dtype=np.float32)
-    if q32.ndim != 2 or q32.shape[1] != 4:
-        raise ValueError("dq_moment_sums: q must be (N, 4)")
+    if q32.ndim == 2:
+        q32 = q32[None]
+    if q32.ndim != 3 or q32.shape[2] != 4:
+        raise ValueError("dq_moment_sums: q must be (N, 4) or (nReplicas, N, 4)")
     lags = np.ascontiguousarray(lags, dtype=np.int64)
-    N = q32.shape[0]
+    nRep, N = q32.shape[:2]
     if lags.size == 0 or lags.min() < 1 or lags.max() >= N:
         raise ValueError("dq_moment_sums: lags must lie in [1, N)")
     nCh = max(1, int(nchunk))
     qd = torch.from_numpy(q32).cuda()
     ld = torch.from_numpy(lags).cuda()
     M = torch.empty((lags.size, nCh, 6), dtype=torch.float64, device=qd.device)
-    _lib.check(lib.sr_dq_moments(qd.data_ptr(), N, ld.data_ptr(), lags.size, int(lags.min()), nCh, M.data_ptr(),
-                                 _lib.current_stream_ptr()), "sr_dq_moments")
-    n = N - lags
+    for r in range(nRep):
+        _lib.check(lib.sr_dq_moments_pooled(qd[r].data_ptr(), N, ld.data_ptr(), lags.size, int(lags.min()), nCh, r, nRep,
+                                            1 if r > 0 else 0, M.data_ptr(), _lib.current_stream_ptr()),
+                   "sr_dq_moments_pooled")
+    n = (N - lags) * nRep
     nb = -(-n // nCh)
     k = np.arange(nCh)[None, :]
     counts = np.clip(np.minimum(n[:, None], nb[:, None] * (k + 1)) - nb[:, None] * k, 0, None)
     return M.cpu().numpy(), n, counts
+
+
+def dq_histogram3d(q, delta, nbins=101):
+    """np.histogramdd(v_dq, range=[(-1,1)]*3, bins=(nbins,)*3, density=True) of the --hist option
+    (calculate-dq-distribution.py:527-528, 633-634; `normed=True` there is the pre-1.24 spelling of density).
+    Returns (hist (nbins,)*3 float64, edges [3 x (nbins+1,)])."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    q32 = np.ascontiguousarray(q, dtype=np.float32)
+    N = q32.shape[0]
+    edges = np.linspace(-1.0, 1.0, nbins + 1)
+    qd = torch.from_numpy(q32).cuda()
+    ed = torch.from_numpy(edges).cuda()
+    counts = torch.zeros((nbins, nbins, nbins), dtype=torch.int32, device=qd.device)
+    cap = 1 << 16
+    amb = torch.empty(cap, dtype=torch.int64, device=qd.device)
+    namb = torch.zeros(1, dtype=torch.int32, device=qd.device)
+    _lib.check(lib.sr_dq_hist3d(qd.data_ptr(), N, int(delta), ed.data_ptr(), nbins, counts.data_ptr(), amb.data_ptr(), cap,
+                                namb.data_ptr(), _lib.current_stream_ptr()), "sr_dq_hist3d")
+    c = counts.cpu().numpy().astype(np.float64)
+    k = int(namb.item())
+    if k > cap:
+        raise _lib.SpinRelaxError("dq_histogram3d: %d edge-ambiguous samples exceed the list capacity" % k)
+    if k:   # samples within 4 ulp of a bin edge (or NaN): NumPy's own arithmetic decides
+        t = amb[:k].cpu().numpy()
+        v = obtain_self_dq(q32, delta)[t, 1:4]
+        extra, _ = np.histogramdd(v, range=[(-1, 1)] * 3, bins=(nbins,) * 3)
+        c += extra
+    s = c.sum()
+    hist = c / (s * np.prod([np.diff(edges)[0]] * 3)) if s > 0 else c
+    return hist, [edges, edges.copy(), edges.copy()]
 
 
 def _vec_moment_sums(vq, nchunk=1):
@@ -125,7 +162,8 @@ def lag_grid(times, min_dt, max_dt, skip_dt):
 
 
 def dq_curves(q, lags, ddt, nchunk=0, do_aniso=True):
-    """All per-lag outputs of the reference's main loop from one GPU pass over the lag list."""
+    """All per-lag outputs of the reference's main loop from one GPU pass over the lag list (q may hold several
+    replica trajectories, see dq_moment_sums)."""
     lags = np.asarray(lags, dtype=np.int64)
     nl = len(lags)
     nCh = nchunk if nchunk > 1 else 1
@@ -316,11 +354,12 @@ def build_parser():
                                 'a time-series of quaternion representation of orientations '
                                 'then manipulate them in various ways',
                                 formatter_class=argparse.ArgumentDefaultsHelpFormatter)
-    p.add_argument('-f', '--infn', type=str, dest='infn', default='colvar-q',
-                   help='Input file in PLUMED quaternion form. Assumes that dt is identical between every frame!')
+    p.add_argument('-f', '--infn', type=str, dest='infn', default=['colvar-q'], nargs='+',
+                   help='Input file(s) in PLUMED quaternion form. Assumes that dt is identical between every frame! '
+                        'Several equally long files are pooled as replicas (calculate-dq-distribution-multi.py).')
     p.add_argument('-o', '--outpref', type=str, dest='out_pref', default='out', help='Output file prefix.')
     p.add_argument('--hist', dest='bDoHist', action='store_true', default=False,
-                   help='3D-histogram of dq at each delay time (not supported: broken upstream on NumPy >= 1.24).')
+                   help='Record the 3D-histogram of rotation-quaternions dq at each delay time, dt.')
     p.add_argument('-o2', '--outtype', type=str, dest='out_suff', default='dat')
     p.add_argument('--iso', dest='bDoIso', action='store_true', default=False,
                    help='Record the isotropic decay of dq.')
@@ -346,11 +385,16 @@ def main(argv=None):
     if args.out_suff not in ("dx", "dat", "none"):
         print("= = ERROR in input: histogram output type must be either dx, or dat, or none.")
         sys.exit()
-    if args.bDoHist:
-        print("= = ERROR: --hist is not available (np.histogramdd(normed=) no longer exists upstream either).",
-              file=sys.stderr)
-        sys.exit(2)
-    fields, data = io_formats.read_from_plumedprint(args.infn)
+    infn = [args.infn] if isinstance(args.infn, str) else list(args.infn)
+    fields, data = io_formats.read_from_plumedprint(infn[0])
+    replicas = [data]
+    for fn in infn[1:]:
+        _, d = io_formats.read_from_plumedprint(fn)
+        if d.shape != data.shape:
+            print("= = ERROR: replica trajectories must have identical lengths (%s vs %s)." % (d.shape, data.shape),
+                  file=sys.stderr)
+            sys.exit(1)
+        replicas.append(d)
     nfield, ndat = data.shape
     print("= = Input data found to be %i fields and %i entries. = =" % (nfield, ndat))
     qprev = data[1:5, 0]
@@ -368,7 +412,23 @@ def main(argv=None):
     lags = np.arange(min_int, max_int + 1, skip_int)
     nch = args.num_chunk
     sub = nch > 1
-    res = dq_curves(np.ascontiguousarray(data[1:5].T), lags, ddt, nch, do_aniso=args.bDoAniso)
+    qall = np.stack([np.ascontiguousarray(d[1:5].T) for d in replicas])
+    res = dq_curves(qall if len(replicas) > 1 else qall[0], lags, ddt, nch, do_aniso=args.bDoAniso)
+    if args.bDoHist and args.out_suff != "none":
+        if len(replicas) > 1:
+            print("= = ERROR: --hist works on a single trajectory.", file=sys.stderr)
+            sys.exit(1)
+        for delta in lags:                                                     # :632-647
+            hist3, edges3 = dq_histogram3d(qall[0], int(delta), args.num_bins)
+            out_file = args.out_pref + "-hist-" + str(delta * ddt) + "ps." + args.out_suff
+            if out_file.endswith("dx"):
+                xmin = [(e[0] + e[1]) / 2.0 for e in edges3]
+                abc = np.zeros((3, 3))
+                for i in range(3):
+                    abc[i][i] = (edges3[i][-1] - edges3[i][0]) / args.num_bins
+                io_formats.write_to_dx(out_file, hist3, (args.num_bins,) * 3, xmin, abc, 'nm')
+            else:
+                io_formats.print_gplot_hist(out_file, hist3, edges3)
     dt = res["dt"]
     time_chk1 = time.time()
     pref = args.out_pref

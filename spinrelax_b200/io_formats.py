@@ -148,3 +148,33 @@ def print_gplot_hist(fn, hist, edges, header='', bSphere=False):
         for i in range(nb[0]):
             row(ctr[0][i], hist[i])
         row(ctr[0][0] + 2 * np.pi, hist[0])
+
+
+def write_to_dx(fname, data, dims, orig, abc, units='A', bScaleDat=True):
+    """OpenDX scalar grid (dxio.py:79-120): header, then the values in C order, three per line."""
+    if units == 'A':
+        scale = 10.0
+    elif units == 'nm':
+        scale = 1.0
+    else:
+        print("= = ERROR in dxio.py - write_to_dx: units argument of write_to_dx accepts only 'nm' and 'A'!")
+        return
+    if dims[0] != data.shape[0] or dims[1] != data.shape[1] or dims[2] != data.shape[2]:
+        print("= = ERROR in dxio.py - write_to_dx: Data dimensions do not match with the matrix dimenstions!")
+        print(dims, data.shape)
+        return
+    outabc = np.multiply(scale, abc)
+    outorig = np.multiply(scale, orig)
+    with open(fname, 'w') as fp:
+        print('#DX-file written by dxio.py', file=fp)
+        print('object 1 class gridpositions counts %i %i %i' % (dims[0], dims[1], dims[2]), file=fp)
+        print('origin %g %g %g' % (outorig[0], outorig[1], outorig[2]), file=fp)
+        for i in range(3):
+            print('delta %g %g %g' % (outabc[i, 0], outabc[i, 1], outabc[i, 2]), file=fp)
+        print('object 2 class gridpositions counts %i %i %i' % (dims[0], dims[1], dims[2]), file=fp)
+        print('object 3 class array type double rank 0 items %i data follows' % (dims[0] * dims[1] * dims[2]), file=fp)
+        flat = np.multiply(1.0 / scale ** 3, data.flatten(order='C')) if bScaleDat else data.flatten(order='C')
+        for pos in range(0, len(flat), 3):
+            print(" ".join("%g" % v for v in flat[pos:pos + 3]), file=fp)
+        print('', file=fp)
+        print('object "density [%s^-3]" class field' % units, file=fp)

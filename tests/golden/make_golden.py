@@ -202,6 +202,33 @@ def _synthetic_curves(n_res, n_pts, seed):
     return t, np.array(Ct), np.array(dCt), truth
 
 
+def golden_dq_multi(refdq):
+    """Replica pooling of calculate-dq-distribution-multi.py:529-540 (that script imports a missing `xvgio` and cannot
+    run, so its loop body is replayed here with the REAL helper functions it shares with calculate-dq-distribution.py:
+    per replica obtain_self_dq, concatenate, then the pooled averages), and the --hist 3-D histogram (:633-634) with
+    `density=True` in place of the removed `normed=True`."""
+    reps = np.stack([synth.quaternion_walk(3000, seed=synth.BASE_SEED + 60 + r, sigma=(0.01, 0.015, 0.03)) for r in range(3)])
+    lags = [1, 7, 50, 333, 1499]
+    nch = 4
+    rec = dict(iso=[], moi=[], chunk_iso=[], chunk_moi=[])
+    for d in lags:
+        v = np.concatenate([refdq.obtain_self_dq(reps[r], d)[..., 1:4] for r in range(3)], axis=0)
+        n = len(v)
+        rec["iso"].append(refdq.average_LegendreP1quat(n, v))
+        rec["moi"].append(refdq.average_anisotropic_tensor(n, v))
+        rec["chunk_iso"].append(refdq.average_LegendreP1quat_chunk(n, v, nch))
+        rec["chunk_moi"].append(refdq.average_anisotropic_tensor_chunk(n, v, nch))
+    hists = {}
+    for d, nb in ((50, 21), (333, 101)):
+        v = refdq.obtain_self_dq(reps[0], d)[..., 1:4]
+        h, e = np.histogramdd(v, range=[(-1, 1)] * 3, bins=(nb, nb, nb), density=True)
+        nz = np.nonzero(h)
+        hists["hist_%d_idx" % d] = np.stack(nz, axis=1).astype(np.int32)
+        hists["hist_%d_val" % d] = h[nz]
+        hists["hist_%d_nb" % d] = np.array(nb)
+    save("dq_multi.npz", q=reps, lags=np.array(lags), nchunk=nch, **{k: np.array(v) for k, v in rec.items()}, **hists)
+
+
 def golden_fit():
     fitCt = ref_loader.module("fitting_Ct_functions")
     t, Ct, dCt, _ = _synthetic_curves(9, 250, synth.BASE_SEED + 41)
@@ -406,6 +433,7 @@ def main():
     golden_traj(refct)
     golden_hist(refct)
     golden_dq(refdq)
+    golden_dq_multi(refdq)
     golden_fit()
     golden_relax()
     golden_relax_cli()

@@ -133,3 +133,43 @@ def _isnum(t):
         return True
     except ValueError:
         return False
+
+
+def test_dq_pooled_replicas_match_reference(golden):
+    """Replica pooling (calculate-dq-distribution-multi.py:529-540): pooled moments and pooled sub-chunks."""
+    from spinrelax_b200 import dq
+    g = golden("dq_multi.npz")
+    nch = int(g["nchunk"])
+    M, n, counts = dq.dq_moment_sums(g["q"], g["lags"], nch)
+    assert np.array_equal(n, 3 * (g["q"].shape[1] - g["lags"]))
+    for k in range(len(g["lags"])):
+        full = M[k].sum(axis=0)
+        assert np.isclose(dq._iso_shipped(full), g["iso"][k], rtol=RTOL_MOMENT)
+        assert np.allclose(dq._sym3(full) / n[k], g["moi"][k], rtol=RTOL_MOMENT, atol=1e-20)
+        assert np.allclose(dq._iso_shipped(M[k]), g["chunk_iso"][k], rtol=RTOL_MOMENT)
+        for c in range(nch):
+            assert np.allclose(dq._sym3(M[k, c]) / counts[k, c], g["chunk_moi"][k][c], rtol=RTOL_MOMENT, atol=1e-20)
+    # one replica per call == all replicas in one call (the all-reduce formulation)
+    parts = [dq.dq_moment_sums(g["q"][r], g["lags"], 1)[0] for r in range(3)]
+    assert np.allclose(sum(parts)[:, 0], M.sum(axis=1), rtol=1e-13)
+
+
+def test_dq_histogram3d_matches_reference(golden, tmp_path):
+    """--hist: counts identical to np.histogramdd, density normalisation, dx / gnuplot writers."""
+    from spinrelax_b200 import dq, io_formats
+    g = golden("dq_multi.npz")
+    for d in (50, 333):
+        nb = int(g["hist_%d_nb" % d])
+        h, edges = dq.dq_histogram3d(g["q"][0], d, nb)
+        idx = g["hist_%d_idx" % d]
+        assert h.shape == (nb, nb, nb)
+        assert np.array_equal(np.stack(np.nonzero(h), axis=1), idx)
+        assert np.allclose(h[tuple(idx.T)], g["hist_%d_val" % d], rtol=1e-14)
+        assert np.array_equal(edges[0], np.linspace(-1, 1, nb + 1))
+    h, edges = dq.dq_histogram3d(g["q"][0], 50, 21)
+    ho, eo = dq_oracle.dq_histogram3d(g["q"][0], 50, 21)
+    io_formats.write_to_dx(str(tmp_path / "h.dx"), h, (21, 21, 21), [-1 + 1 / 21.] * 3, np.eye(3) * 2 / 21., 'nm')
+    txt = (tmp_path / "h.dx").read_text().splitlines()
+    assert txt[1] == "object 1 class gridpositions counts 21 21 21" and txt[-1] == 'object "density [nm^-3]" class field'
+    vals = np.array(" ".join(txt[8:-2]).split(), dtype=float)
+    assert vals.size == 21 ** 3 and np.allclose(vals, ho.ravel(), rtol=1e-5, atol=1e-12)

@@ -192,3 +192,21 @@ def test_traj_oracle_matches_reference(golden):
         Rp = R @ (np.eye(3) + K + 0.5 * K @ K)
         rp = np.sqrt(((np.einsum("fab,fib->fia", Rp, x) - y[None]) ** 2).sum(-1).mean(-1))
         assert np.all(rp >= rmsd - 1e-12)
+
+
+def test_dq_pooled_and_hist3d_match_reference(golden):
+    from oracle import dq_oracle
+    g = golden("dq_multi.npz")
+    nch = int(g["nchunk"])
+    for k, d in enumerate(g["lags"]):
+        v = dq_oracle.pooled_vectors(g["q"], int(d))
+        assert np.isclose(dq_oracle.iso_moment_shipped(v), g["iso"][k], rtol=1e-12)
+        assert np.allclose(dq_oracle.aniso_tensor(v), g["moi"][k], rtol=1e-12, atol=1e-20)
+        assert np.allclose(dq_oracle.iso_moment_chunks(v, nch), g["chunk_iso"][k], rtol=1e-12)
+        assert np.allclose(dq_oracle.aniso_tensor_chunks(v, nch), g["chunk_moi"][k], rtol=1e-12, atol=1e-20)
+    for d in (50, 333):
+        nb = int(g["hist_%d_nb" % d])
+        h, _ = dq_oracle.dq_histogram3d(g["q"][0], d, nb)
+        idx = g["hist_%d_idx" % d]
+        assert np.array_equal(np.stack(np.nonzero(h), axis=1), idx)
+        assert np.array_equal(h[tuple(idx.T)], g["hist_%d_val" % d])
