@@ -241,6 +241,17 @@ def run_ours(args):
     barrier()
     e2e_s = (time.perf_counter() - t0)
 
+    # the reference-signature drop-in itself: calculate_Ct_Palmer(vecs) on an ordinary (pageable) NumPy array through
+    # the single C-ABI host call sr_ct_palmer_host (C(t) only: the histogram is a separate call in the reference too)
+    dropin_s = None
+    if world == 1:
+        v_page = np.array(v_np)                      # pageable copy
+        ct.calculate_Ct_Palmer_quiet(v_page)                # warm-up: sizes the library's scratch cache
+        t0 = time.perf_counter()
+        ct.calculate_Ct_Palmer_quiet(v_page)
+        dropin_s = time.perf_counter() - t0
+        del v_page
+
     t = torch.tensor([ms_total, e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -273,6 +284,10 @@ def run_ours(args):
                         "steps": e2e_steps, "api": "spinrelax_b200.pipeline.CtHistStep.run_host: pinned NumPy in -> per-chunk H2D pipelined with "
                         "sr_pack_vectors_f32_chunks, sr_ct_lag_sums_chunks -> sr_ct_palmer_finalize, sr_sphere_hist (C ABI) -> D2H"},
                 "gpu_launches": step.launches_per_step() * args.steps, "roofline": roof, "cpu_baseline": cpu}
+        if dropin_s is not None:
+            line["e2e_dropin"] = {"value": pairs_gpu / dropin_s, "unit": UNIT, "seconds": dropin_s,
+                                  "api": "spinrelax_b200.ct.calculate_Ct_Palmer(vecs) on a pageable NumPy array -> "
+                                         "sr_ct_palmer_host (C ABI, pinned staging + chunk pipelining inside)"}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -85,8 +85,11 @@ int sr_ct_palmer_finalize(const double* d_S, int nC, long long nF, int nR, long 
 int sr_ct_palmer_device(const float* d_vecs, int nC, long long nF, int nR, float* d_Ct, float* d_dCt,
                         void* d_workspace, size_t workspace_bytes, void* stream);
 
-/* Same through host buffers: H2D of vecs, compute, D2H of Ct/dCt (allocates its own scratch). */
+/* Same through host (pageable) buffers: pinned staging, H2D of chunk c + 1 overlapped with the kernels of chunk c,
+ * D2H of Ct/dCt.  Scratch (device buffers, pinned staging, streams) is cached between calls; sr_release_host_cache()
+ * frees it.  Calls are serialised by an internal mutex. */
 int sr_ct_palmer_host(const float* h_vecs, int nC, long long nF, int nR, float* h_Ct, float* h_dCt);
+void sr_release_host_cache(void);
 
 /* ------------------------------------------------------------------------------------------------
  * K3: PAF rotation + Lambert-cylindrical histogram, replaces calculate-Ct-from-traj.py:567 (rotation,

@@ -33,6 +33,7 @@ def _declare(lib):
         "sr_ct_palmer_finalize": (i, [vp, i, ll, i, ll, vp, vp, vp]),
         "sr_ct_palmer_device": (i, [vp, i, ll, i, vp, vp, vp, sz, vp]),
         "sr_ct_palmer_host": (i, [vp, i, ll, i, vp, vp]),
+        "sr_release_host_cache": (None, []),
         "sr_sphere_hist_table_doubles": (i, [i, i]),
         "sr_vec_block_moments": (i, [vp, ll, i, ll, vp, vp]),
         "sr_rotate_vectors_f32_f64": (i, [vp, ll, dp, vp, vp]),

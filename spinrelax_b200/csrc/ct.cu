@@ -2,6 +2,9 @@
 // Reference arithmetic: calculate_Ct_Palmer, calculate-Ct-from-traj.py:200-238.
 #include "common.cuh"
 
+#include <algorithm>
+#include <mutex>
+
 namespace {
 
 // ------------------------------------------------------------------------------------------------
@@ -460,32 +463,111 @@ extern "C" int sr_ct_palmer_device(const float* d_vecs, int nC, long long nF, in
   return sr_ct_palmer_finalize(S, nC, nF, nR, L, d_Ct, d_dCt, stream);
 }
 
+// Host-buffer entry point.  The caller's array is ordinary pageable memory, so it is staged through two pinned
+// buffers on a copy stream; chunk 0 is uploaded first and its K2 / K1 run while the remaining chunks are still on
+// their way (the same two-stage schedule as the Python pipeline).  Device buffers, pinned staging buffers, streams
+// and events are kept in a grow-only cache between calls (cudaMalloc / cudaFree of gigabytes cost tens of
+// milliseconds each); sr_release_host_cache() returns them.
+namespace {
+struct HostCallCache {
+  std::mutex mu;
+  int device = -1;
+  char* d_buf = nullptr; size_t d_cap = 0;
+  char* stage[2] = {nullptr, nullptr}; size_t stage_cap = 0;
+  cudaStream_t copy = nullptr, comp = nullptr;
+  cudaEvent_t freed[2] = {nullptr, nullptr}, ready[2] = {nullptr, nullptr};
+  void release() {
+    if (d_buf) cudaFree(d_buf);
+    for (int i = 0; i < 2; ++i) {
+      if (stage[i]) cudaFreeHost(stage[i]);
+      if (freed[i]) cudaEventDestroy(freed[i]);
+      if (ready[i]) cudaEventDestroy(ready[i]);
+      stage[i] = nullptr; freed[i] = ready[i] = nullptr;
+    }
+    if (copy) cudaStreamDestroy(copy);
+    if (comp) cudaStreamDestroy(comp);
+    d_buf = nullptr; d_cap = stage_cap = 0; copy = comp = nullptr; device = -1;
+  }
+};
+HostCallCache g_host_cache;
+}  // namespace
+
+extern "C" void sr_release_host_cache(void) {
+  std::lock_guard<std::mutex> lock(g_host_cache.mu);
+  g_host_cache.release();
+}
+
 extern "C" int sr_ct_palmer_host(const float* h_vecs, int nC, long long nF, int nR, float* h_Ct, float* h_dCt) {
   SR_REQUIRE(h_vecs && h_Ct && h_dCt, "sr_ct_palmer_host: null pointer");
   SR_REQUIRE(nC > 0 && nR > 0 && nF >= 2, "sr_ct_palmer_host: bad shape");
   const long long L = nF / 2;
-  const size_t in_bytes = (size_t)nC * nF * nR * 3 * sizeof(float);
-  const size_t out_bytes = (size_t)L * nR * sizeof(float);
+  const size_t chunk_bytes = (size_t)nF * nR * 3 * sizeof(float);
+  const size_t in_bytes = (size_t)sr_round_up((long long)((size_t)nC * chunk_bytes), 256);
+  const size_t out_bytes = (size_t)sr_round_up((long long)((size_t)L * nR * sizeof(float)), 256);
   const size_t ws_bytes = sr_ct_workspace_bytes(nC, nF, nR);
-  float *d_in = nullptr, *d_Ct = nullptr, *d_dCt = nullptr;
-  void* d_ws = nullptr;
-  int rc = SR_OK;
-  cudaError_t e;
-  if ((e = cudaMalloc(&d_in, in_bytes)) != cudaSuccess || (e = cudaMalloc(&d_Ct, out_bytes)) != cudaSuccess ||
-      (e = cudaMalloc(&d_dCt, out_bytes)) != cudaSuccess || (e = cudaMalloc(&d_ws, ws_bytes)) != cudaSuccess) {
-    sr_set_error("sr_ct_palmer_host: cudaMalloc failed: %s", cudaGetErrorString(e));
+  const size_t need = in_bytes + 2 * out_bytes + ws_bytes;
+  const size_t stage_bytes = (size_t)32 << 20;
+  const long long pitch = sr_ct_row_pitch(nF);
+  HostCallCache& hc = g_host_cache;
+  std::lock_guard<std::mutex> lock(hc.mu);
+  int rc = SR_OK, dev = 0;
+  cudaError_t e = cudaSuccess;
+  auto fail = [&](const char* what) {
+    sr_set_error("sr_ct_palmer_host: %s failed: %s", what, cudaGetErrorString(e));
     rc = SR_ERR_CUDA;
+  };
+  SR_CUDA(cudaGetDevice(&dev));
+  if (hc.device != dev) { hc.release(); hc.device = dev; }
+  if (hc.d_cap < need) {
+    if (hc.d_buf) cudaFree(hc.d_buf);
+    hc.d_buf = nullptr; hc.d_cap = 0;
+    if ((e = cudaMalloc(&hc.d_buf, need)) != cudaSuccess) { fail("cudaMalloc"); return rc; }
+    hc.d_cap = need;
   }
-  if (!rc && (e = cudaMemcpy(d_in, h_vecs, in_bytes, cudaMemcpyHostToDevice)) != cudaSuccess) {
-    sr_set_error("sr_ct_palmer_host: H2D failed: %s", cudaGetErrorString(e));
-    rc = SR_ERR_CUDA;
+  if (!hc.stage[0]) {
+    if ((e = cudaMallocHost(&hc.stage[0], stage_bytes)) != cudaSuccess || (e = cudaMallocHost(&hc.stage[1], stage_bytes)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&hc.copy, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&hc.comp, cudaStreamNonBlocking)) != cudaSuccess) { fail("allocation"); hc.release(); return rc; }
+    hc.stage_cap = stage_bytes;
+    for (int i = 0; i < 2; ++i)
+      if ((e = cudaEventCreateWithFlags(&hc.freed[i], cudaEventDisableTiming)) != cudaSuccess ||
+          (e = cudaEventCreateWithFlags(&hc.ready[i], cudaEventDisableTiming)) != cudaSuccess) { fail("cudaEventCreate"); hc.release(); return rc; }
   }
-  if (!rc) rc = sr_ct_palmer_device(d_in, nC, nF, nR, d_Ct, d_dCt, d_ws, ws_bytes, nullptr);
-  if (!rc && ((e = cudaMemcpy(h_Ct, d_Ct, out_bytes, cudaMemcpyDeviceToHost)) != cudaSuccess ||
-              (e = cudaMemcpy(h_dCt, d_dCt, out_bytes, cudaMemcpyDeviceToHost)) != cudaSuccess)) {
-    sr_set_error("sr_ct_palmer_host: D2H failed: %s", cudaGetErrorString(e));
-    rc = SR_ERR_CUDA;
+  float* d_in = (float*)hc.d_buf;
+  float* d_Ct = (float*)(hc.d_buf + in_bytes);
+  float* d_dCt = (float*)(hc.d_buf + in_bytes + out_bytes);
+  char* d_ws = hc.d_buf + in_bytes + 2 * out_bytes;
+  void* packed = d_ws;
+  double* S = (double*)(d_ws + sr_round_up((long long)((size_t)nR * nC * pitch * 12), 256));
+  // upload groups: chunk 0, then chunks 1 .. nC-1
+  const int nGroups = nC > 1 ? 2 : 1;
+  size_t done = 0;
+  int piece = 0;
+  for (int g = 0; g < nGroups && !rc; ++g) {
+    const int c0 = g == 0 ? 0 : 1, n = g == 0 ? 1 : nC - 1;
+    const size_t end = (size_t)(c0 + n) * chunk_bytes;
+    while (done < end && !rc) {
+      const size_t len = std::min(hc.stage_cap, end - done);
+      const int b = piece & 1;
+      if (piece >= 2 && (e = cudaEventSynchronize(hc.freed[b])) != cudaSuccess) { fail("cudaEventSynchronize"); break; }
+      memcpy(hc.stage[b], (const char*)h_vecs + done, len);
+      if ((e = cudaMemcpyAsync((char*)d_in + done, hc.stage[b], len, cudaMemcpyHostToDevice, hc.copy)) != cudaSuccess ||
+          (e = cudaEventRecord(hc.freed[b], hc.copy)) != cudaSuccess) { fail("H2D"); break; }
+      done += len; ++piece;
+    }
+    if (rc) break;
+    if ((e = cudaEventRecord(hc.ready[g], hc.copy)) != cudaSuccess ||
+        (e = cudaStreamWaitEvent(hc.comp, hc.ready[g], 0)) != cudaSuccess) { fail("cudaStreamWaitEvent"); break; }
+    rc = sr_pack_vectors_f32_chunks(d_in + (size_t)c0 * (chunk_bytes / sizeof(float)), nC, c0, n, nF, nR, nullptr, packed,
+                                    pitch, hc.comp);
+    if (!rc) rc = sr_ct_lag_sums_chunks(packed, pitch, nC, c0, n, nF, nR, L, S, hc.comp);
   }
-  cudaFree(d_in); cudaFree(d_Ct); cudaFree(d_dCt); cudaFree(d_ws);
+  if (!rc) rc = sr_ct_palmer_finalize(S, nC, nF, nR, L, d_Ct, d_dCt, hc.comp);
+  const size_t out_exact = (size_t)L * nR * sizeof(float);
+  if (!rc && ((e = cudaMemcpyAsync(h_Ct, d_Ct, out_exact, cudaMemcpyDeviceToHost, hc.comp)) != cudaSuccess ||
+              (e = cudaMemcpyAsync(h_dCt, d_dCt, out_exact, cudaMemcpyDeviceToHost, hc.comp)) != cudaSuccess))
+    fail("D2H");
+  cudaStreamSynchronize(hc.copy);
+  if ((e = cudaStreamSynchronize(hc.comp)) != cudaSuccess && !rc) fail("cudaStreamSynchronize");
   return rc;
 }
