@@ -202,3 +202,25 @@ def test_pipeline_host_path_matches_device_path():
     assert rel_err(Ct_h, oCt) < RTOL_CT
     ohist, _ = ct_oracle.sphere_histogram(v4.reshape(nC * nF, nR, 3), np.array(q))
     assert np.array_equal(hist_h, ohist)
+
+
+def test_wide_vector_set_config4_shape():
+    """BASELINE config 4 is wide (1000 N-H + 1000 C-H vectors): 2000 vectors, short chunks -- every vector group,
+    the partial last groups of K2 / K3 and the per-vector rows of K1 against the oracle."""
+    import torch
+    from spinrelax_b200 import hist, synth
+    nC, nF, nR = 2, 300, 2000
+    v4 = synth.nh_vectors(nC * nF, nR, seed=2000).reshape(nC, nF, nR, 3)
+    Ct, dCt = _gpu_ct(v4)
+    oCt, odCt = ct_oracle.ct_palmer(v4.astype(np.float64))
+    assert rel_err(Ct, oCt) < RTOL_CT
+    assert np.max(np.abs(dCt - odCt)) < 2e-6 * max(1e-3, float(np.max(np.abs(odCt))))
+    q = np.array([0.83, -0.31, 0.22, 0.41])
+    for n_sub in (2000, 1999, 1001):                      # nR % 4 != 0 takes the scalar-load kernels
+        sub = np.ascontiguousarray(v4.reshape(nC * nF, nR, 3)[:, :n_sub])
+        h, _ = hist.sphere_histogram(sub, q)
+        ho, _ = ct_oracle.sphere_histogram(sub, q)
+        assert np.array_equal(h.astype(np.int64), ho.astype(np.int64))
+    sub = np.ascontiguousarray(v4[:, :, :1001])
+    Ct2, _ = _gpu_ct(sub)
+    assert np.array_equal(Ct2, Ct[:, :1001])              # rows are independent: same bits whatever the set

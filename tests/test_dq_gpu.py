@@ -173,3 +173,22 @@ def test_dq_histogram3d_matches_reference(golden, tmp_path):
     assert txt[1] == "object 1 class gridpositions counts 21 21 21" and txt[-1] == 'object "density [nm^-3]" class field'
     vals = np.array(" ".join(txt[8:-2]).split(), dtype=float)
     assert vals.size == 21 ** 3 and np.allclose(vals, ho.ravel(), rtol=1e-5, atol=1e-12)
+
+
+def test_dq_full_size_subset_of_lags():
+    """BASELINE config 3 size (1e6 frames): every lag is independent, so a spread subset of lags against the
+    float64 oracle pins the full-size run; plus additivity over sub-chunks for the whole run-all set."""
+    from spinrelax_b200 import dq, synth
+    N = 1000000
+    q = synth.quaternion_walk(N, seed=synth.BASE_SEED + 3, sigma=(0.004, 0.006, 0.012))
+    lags = np.arange(1000, 100001, 1000)
+    M, n, counts = dq.dq_moment_sums(q, lags, 4)
+    M1, _, _ = dq.dq_moment_sums(q, lags, 1)
+    assert np.allclose(M.sum(axis=1), M1[:, 0], rtol=1e-13)
+    assert np.array_equal(counts.sum(axis=1), n)
+    for k in (0, 49, 99):
+        vo = dq_oracle.self_dq(q, int(lags[k]))[..., 1:4]
+        assert np.allclose(dq._sym3(M1[k, 0]), np.einsum("ti,tj->ij", vo, vo), rtol=1e-11, atol=1e-16)
+        nb = -(-len(vo) // 4)
+        blk = vo[nb * 3:]
+        assert np.allclose(dq._sym3(M[k, 3]), np.einsum("ti,tj->ij", blk, blk), rtol=1e-11, atol=1e-16)
