@@ -106,8 +106,8 @@ void sr_release_host_cache(void);
  * FP64 resolve pass then re-examines that list, counts what is farther than tol_phi (rad) / tol_cos from every
  * bin edge and overwrites those entries with -1.  Entries that are still >= 0 afterwards are samples the caller
  * must bin with the reference's exact NumPy formula -- this is what makes the counts bit-identical to the
- * reference without sharing its libm.  A list that was appended to by an earlier call is re-examined against
- * THIS call's d_vecs, so reset *d_amb_count between different arrays.
+ * reference without sharing its libm.  Only the entries appended by this call are re-examined, so counts and the
+ * list may be accumulated over several calls (sample indices are relative to each call's d_vecs).
  * ---------------------------------------------------------------------------------------------- */
 int sr_sphere_hist_table_doubles(int nbx, int nby);
 int sr_sphere_hist(const float* d_vecs, long long nFrames, int nR, const double* h_q_rot, int nbx, int nby,

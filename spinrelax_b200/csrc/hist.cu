@@ -211,16 +211,23 @@ sphere_hist_kernel(const float* __restrict__ vecs, long long nFrames, int nR, in
   }
 }
 
+// remembers where this call's retry entries start (the list may already hold entries of earlier calls)
+__global__ void sphere_hist_mark_kernel(const int* __restrict__ amb_count, int amb_capacity, int* __restrict__ amb_start) {
+  *amb_start = min(*amb_count, amb_capacity);
+}
+
 // Second pass over the fast path's misses (typically ~1e-4 of the samples): FP64 re-examination for the rotated
 // stream, NaN / zero-vector drop for the float32 reference stream.  Resolved entries are overwritten with -1,
 // entries that stay ambiguous keep their sample id for the host tie-break (hist.py::_reference_bins).
 __global__ void __launch_bounds__(256)
 sphere_hist_resolve_kernel(const float* __restrict__ vecs, int nR, HistParams p, const double2* __restrict__ edge_dir,
                            const double* __restrict__ edge_cos, unsigned int* __restrict__ counts,
-                           long long* __restrict__ amb_idx, int amb_capacity, const int* __restrict__ amb_count) {
+                           long long* __restrict__ amb_idx, int amb_capacity, const int* __restrict__ amb_count,
+                           const int* __restrict__ amb_start) {
+  // only the entries appended by THIS call's hot pass: [*amb_start, *amb_count)
   const int n = min(*amb_count, amb_capacity);
   const int nbins = p.nbx * p.nby;
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+  for (int e = *amb_start + blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
     const long long sidx = amb_idx[e];
     if (sidx < 0) continue;
     const float* v = vecs + sidx * 3;
@@ -292,6 +299,9 @@ extern "C" int sr_sphere_hist(const float* d_vecs, long long nFrames, int nR, co
   const double2* edge_dir = (const double2*)d_edge_table;
   const double* edge_cos = d_edge_table + 2 * (nbx + 1);
   cudaStream_t st = (cudaStream_t)stream;
+  int* d_amb_start = nullptr;                       // one int of scratch per call, stream ordered
+  SR_CUDA(cudaMallocAsync(&d_amb_start, sizeof(int), st));
+  sphere_hist_mark_kernel<<<1, 1, 0, st>>>(d_amb_count, amb_capacity, d_amb_start);
   if (nR % 4 == 0 && ((uintptr_t)d_vecs & 15) == 0) {
     SR_CUDA(cudaFuncSetAttribute(sphere_hist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     sphere_hist_kernel<true><<<grid, kHistThreads, smem, st>>>(d_vecs, nFrames, nR, (int)fpb, p, edge_dir, d_counts,
@@ -303,7 +313,8 @@ extern "C" int sr_sphere_hist(const float* d_vecs, long long nFrames, int nR, co
   }
   SR_CUDA(cudaGetLastError());
   sphere_hist_resolve_kernel<<<sms, 256, 0, st>>>(d_vecs, nR, p, edge_dir, edge_cos, d_counts, d_amb_idx, amb_capacity,
-                                                  d_amb_count);
+                                                  d_amb_count, d_amb_start);
   SR_CUDA(cudaGetLastError());
+  SR_CUDA(cudaFreeAsync(d_amb_start, st));
   return SR_OK;
 }

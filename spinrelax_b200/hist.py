@@ -68,13 +68,17 @@ class SphereHistogram:
         self.amb_capacity = amb_capacity
 
     def accumulate_device(self, v_dev, q_rot, reset=True):
-        """v_dev: CUDA float32 (frames, nR, 3). Adds to counts; ambiguous sample ids go to amb_idx."""
+        """v_dev: CUDA float32 (frames, nR, 3). Adds to counts; ambiguous sample ids go to amb_idx.
+        With reset=False the counts of several arrays are accumulated: call resolve_pending(v_dev, q_rot) (or
+        finish) for each array before launching the next one, because the ambiguous ids index into v_dev."""
         torch = self.torch
         if not (v_dev.is_cuda and v_dev.dtype == torch.float32 and v_dev.is_contiguous() and v_dev.shape[1] == self.nR):
             raise _lib.SpinRelaxError("SphereHistogram: need contiguous float32 CUDA (frames, %d, 3)" % self.nR)
         if reset:
             self.counts.zero_()
             self.amb_count.zero_()
+            self._host_extra = None
+            self.last_ambiguous = 0
         tol = TOL_F64 if q_rot is not None else TOL_F32
         q = None if q_rot is None else (ctypes.c_double * 4)(*[float(x) for x in q_rot])
         rc = self.lib.sr_sphere_hist(v_dev.data_ptr(), v_dev.shape[0], self.nR, q, self.nbx, self.nby,
@@ -83,25 +87,32 @@ class SphereHistogram:
                                      _lib.current_stream_ptr())
         _lib.check(rc, "sr_sphere_hist")
 
-    def finish(self, v_dev, q_rot):
-        """Resolve the ambiguous samples with the reference formula and return int64 counts (NumPy)."""
+    def resolve_pending(self, v_dev, q_rot):
+        """Bin the samples the device left undecided (ids >= 0 in the list) with the reference's own NumPy formula;
+        the result is kept on the host and the device list is emptied."""
         n_amb = int(self.amb_count.item())
-        counts = self.counts.cpu().numpy().astype(np.int64)
         if n_amb > self.amb_capacity:
-            raise _lib.SpinRelaxError("SphereHistogram: %d ambiguous samples exceed capacity %d"
+            raise _lib.SpinRelaxError("SphereHistogram: %d retry / ambiguous samples exceed capacity %d"
                                       % (n_amb, self.amb_capacity))
-        self.last_ambiguous = n_amb
+        if getattr(self, "_host_extra", None) is None:
+            self._host_extra = np.zeros((self.nR, self.nbx * self.nby), dtype=np.int64)
         if n_amb:
             idx = self.amb_idx[:n_amb]
             idx = idx[idx >= 0]          # -1 = resolved on the device by sphere_hist_resolve_kernel
-            self.last_ambiguous = int(idx.numel())
-        if n_amb and idx.numel():
-            rows = v_dev.reshape(-1, 3)[idx].cpu().numpy()
-            idx = idx.cpu().numpy()
-            bins = _reference_bins(rows, q_rot, self.edges_phi, self.edges_cos)
-            ok = bins >= 0
-            np.add.at(counts.reshape(self.nR, -1), (idx[ok] % self.nR, bins[ok]), 1)
-        return counts
+            self.last_ambiguous = getattr(self, "last_ambiguous", 0) + int(idx.numel())
+            if idx.numel():
+                rows = v_dev.reshape(-1, 3)[idx].cpu().numpy()
+                idx = idx.cpu().numpy()
+                bins = _reference_bins(rows, q_rot, self.edges_phi, self.edges_cos)
+                ok = bins >= 0
+                np.add.at(self._host_extra, (idx[ok] % self.nR, bins[ok]), 1)
+            self.amb_count.zero_()
+
+    def finish(self, v_dev, q_rot):
+        """Resolve the ambiguous samples of the last array and return int64 counts (NumPy)."""
+        self.resolve_pending(v_dev, q_rot)
+        counts = self.counts.cpu().numpy().astype(np.int64)
+        return counts + self._host_extra.reshape(counts.shape)
 
 
 def sphere_histogram(frames_vecs, q_rot=None, nbins_phi=72):
