@@ -13,6 +13,7 @@
 //      with the reference's own NumPy formula; everything else in the list is overwritten with -1.
 #include "common.cuh"
 #include <algorithm>
+#include <mutex>
 
 namespace {
 
@@ -299,8 +300,18 @@ extern "C" int sr_sphere_hist(const float* d_vecs, long long nFrames, int nR, co
   const double2* edge_dir = (const double2*)d_edge_table;
   const double* edge_cos = d_edge_table + 2 * (nbx + 1);
   cudaStream_t st = (cudaStream_t)stream;
-  int* d_amb_start = nullptr;                       // one int of scratch per call, stream ordered
-  SR_CUDA(cudaMallocAsync(&d_amb_start, sizeof(int), st));
+  // one int of device scratch per call in flight: a small ring allocated once per device.  (cudaMallocAsync is not
+  // an option here: releasing the pool at the caller's next synchronisation costs ~0.4 s next to torch's allocator.)
+  static std::mutex ring_mu;
+  static int* ring[64] = {nullptr};
+  static unsigned ring_next[64] = {0};
+  int* d_amb_start = nullptr;
+  {
+    std::lock_guard<std::mutex> lock(ring_mu);
+    SR_REQUIRE(dev >= 0 && dev < 64, "sr_sphere_hist: device ordinal %d not supported", dev);
+    if (!ring[dev]) SR_CUDA(cudaMalloc(&ring[dev], 256 * sizeof(int)));
+    d_amb_start = ring[dev] + (ring_next[dev]++ & 255u);
+  }
   sphere_hist_mark_kernel<<<1, 1, 0, st>>>(d_amb_count, amb_capacity, d_amb_start);
   if (nR % 4 == 0 && ((uintptr_t)d_vecs & 15) == 0) {
     SR_CUDA(cudaFuncSetAttribute(sphere_hist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -315,6 +326,5 @@ extern "C" int sr_sphere_hist(const float* d_vecs, long long nFrames, int nR, co
   sphere_hist_resolve_kernel<<<sms, 256, 0, st>>>(d_vecs, nR, p, edge_dir, edge_cos, d_counts, d_amb_idx, amb_capacity,
                                                   d_amb_count, d_amb_start);
   SR_CUDA(cudaGetLastError());
-  SR_CUDA(cudaFreeAsync(d_amb_start, st));
   return SR_OK;
 }
