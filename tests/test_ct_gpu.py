@@ -125,6 +125,28 @@ def test_error_codes():
     import torch
     x = torch.zeros(16, device="cuda")
     assert lib.sr_ct_palmer_device(x.data_ptr(), 1, 100, 1, x.data_ptr(), x.data_ptr(), x.data_ptr(), 8, None) == -3
+    # chunk-range entry points: range outside [0, nC), misaligned packed stream
+    big = torch.zeros(1 << 16, device="cuda")
+    pitch = lib.sr_ct_row_pitch(100)
+    assert lib.sr_pack_vectors_f32_chunks(big.data_ptr(), 2, 1, 2, 100, 1, None, big.data_ptr(), pitch, None) == -1
+    assert b"chunk range" in lib.sr_last_error()
+    assert lib.sr_ct_lag_sums_chunks(big.data_ptr() + 4, pitch, 2, 0, 1, 100, 1, 50, big.data_ptr(), None) == -1
+    assert b"aligned" in lib.sr_last_error()
+    assert lib.sr_ct_lag_sums_chunks(big.data_ptr(), pitch, 2, 2, 1, 100, 1, 50, big.data_ptr(), None) == -1
+    # front end, dq extras
+    idx = torch.zeros(4, dtype=torch.int32, device="cuda")
+    assert lib.sr_xh_vectors(big.data_ptr(), 10, 5, idx.data_ptr(), idx.data_ptr(), 0, big.data_ptr(), None) == -1
+    assert lib.sr_xh_vectors_superposed(big.data_ptr(), 10, 5, idx.data_ptr(), big.data_ptr(), 2, idx.data_ptr(),
+                                        idx.data_ptr(), 4, big.data_ptr(), None, None) == -1
+    assert b"3 fit atoms" in lib.sr_last_error()
+    lags = torch.ones(1, dtype=torch.int64, device="cuda")
+    assert lib.sr_dq_moments_pooled(big.data_ptr(), 100, lags.data_ptr(), 1, 1, 1, 3, 3, 0, big.data_ptr(), None) == -1
+    assert b"replica" in lib.sr_last_error()
+    assert lib.sr_dq_hist3d(big.data_ptr(), 100, 1, big.data_ptr(), 4096, big.data_ptr(), big.data_ptr(), 8, big.data_ptr(),
+                            None) == -1
+    from spinrelax_b200 import traj
+    with pytest.raises(_lib.SpinRelaxError):            # atom index outside the trajectory
+        traj.xh_vectors_device(torch.zeros((3, 5, 3), device="cuda"), [7], [0])
 
 
 def test_s2_and_average_vector(golden):
