@@ -32,7 +32,7 @@ class CtHistStep:
             from . import hist as _hist
             self._hist = _hist.SphereHistogram(nR, self.nbx, device=self.dev)
         self._events = {}
-        self._launches = 3 + (2 if self.has_hist else 0)   # pack, lag sums, finalize (+ histogram, resolve)
+        self._launches = 3 + (3 if self.has_hist else 0)   # pack, lag sums, finalize (+ mark, histogram, resolve)
 
     # -------------------------------------------------------------------------------------------
     def _timed(self, name, fn, on):
