@@ -270,15 +270,16 @@ ct_finalize_kernel(const double* __restrict__ S, int nC, int nF, int nR, int L, 
     float m32 = 0.f, s32 = 0.f;
     if (r < nR && di < L) {
       const double* row = S + (long long)r * nC * L + di;
-      double mean = 0.0;
-      for (int c = 0; c < nC; ++c) mean += -0.5 + row[(long long)c * L] * inv;
-      mean /= nC;
-      double var = 0.0;   // two-pass: the chunk means differ by ~1e-2 of their value
-      for (int c = 0; c < nC; ++c) {
-        const double m = -0.5 + row[(long long)c * L] * inv;
-        var += (m - mean) * (m - mean);
+      // one pass over S: shifted sums (shift = first chunk's value) keep sum((m - mean)^2) free of cancellation
+      const double m0 = -0.5 + row[0] * inv;
+      double s1 = 0.0, s2 = 0.0;
+      for (int c = 1; c < nC; ++c) {
+        const double d = (-0.5 + row[(long long)c * L] * inv) - m0;
+        s1 += d; s2 = fma(d, d, s2);
       }
-      var /= nC;
+      const double dm = s1 / nC;
+      const double mean = m0 + dm;
+      const double var = fmax(0.0, s2 / nC - dm * dm);
       m32 = (float)mean;
       s32 = (float)(sqrt(var) / (sqrt((double)nC) - 1.0));
     }
