@@ -316,12 +316,17 @@ using CtV9 = CtCfg<19, 4, 2, 12, 1, 4>;
 using CtV10 = CtCfg<19, 6, 1, 12, 1, 3>;
 using CtV11 = CtCfg<17, 6, 2, 12, 1, 3>;
 using CtV12 = CtCfg<15, 8, 1, 8, 2, 3>;
-constexpr int kNumVariants = 13;
-constexpr int kLongVariant = 4;      // R = 19, 12 warps, 1 CTA/SM, 3 stages: 38 terms per FP32 partial sum
+using CtV13 = CtCfg<19, 6, 3, 12, 1, 4>;
+using CtV14 = CtCfg<19, 3, 3, 12, 1, 4>;
+using CtV15 = CtCfg<19, 6, 3, 12, 1, 3>;
+using CtV16 = CtCfg<17, 6, 3, 12, 1, 3>;
+using CtV17 = CtCfg<21, 6, 3, 12, 1, 3>;
+constexpr int kNumVariants = 18;
+constexpr int kLongVariant = 13;     // R = 19, 12 warps, 1 CTA/SM, 4 stages: 57 terms per FP32 partial sum
 constexpr int kShortVariant = 12;    // R = 15, 8 warps, 2 CTAs/SM, 3 stages: 15 terms per FP32 partial sum (few chunk
                                      // means enter dCt when chunks are short, so keep its rounding at the 1e-7 level)
 constexpr long long kShortFrames = 8192;
-constexpr int kMaxTF = 1440, kMaxTL = 32 * 21;   // padding must cover the largest tile of any variant
+constexpr int kMaxTF = 1536, kMaxTL = 32 * 21;   // padding must cover the largest tile of any variant
 
 template <class Cfg>
 int launch_ct_lag(const float* U, long long pitch, long long nF, int nR, int nC, int c0, int nCsub, long long L, double* S,
@@ -410,6 +415,11 @@ static int ct_lag_sums_impl(const void* d_packed, long long pitch, int nC, int c
     case 10: return launch_ct_lag<CtV10>(U, pitch, nF, nR, nC, c0, nCsub, L, d_S, st);
     case 11: return launch_ct_lag<CtV11>(U, pitch, nF, nR, nC, c0, nCsub, L, d_S, st);
     case 12: return launch_ct_lag<CtV12>(U, pitch, nF, nR, nC, c0, nCsub, L, d_S, st);
+    case 13: return launch_ct_lag<CtV13>(U, pitch, nF, nR, nC, c0, nCsub, L, d_S, st);
+    case 14: return launch_ct_lag<CtV14>(U, pitch, nF, nR, nC, c0, nCsub, L, d_S, st);
+    case 15: return launch_ct_lag<CtV15>(U, pitch, nF, nR, nC, c0, nCsub, L, d_S, st);
+    case 16: return launch_ct_lag<CtV16>(U, pitch, nF, nR, nC, c0, nCsub, L, d_S, st);
+    case 17: return launch_ct_lag<CtV17>(U, pitch, nF, nR, nC, c0, nCsub, L, d_S, st);
     default: break;
   }
   sr_set_error("sr_ct_lag_sums_variant: unknown variant %d (have %d)", variant, kNumVariants);
