@@ -114,6 +114,13 @@ int sr_sphere_hist(const float* d_vecs, long long nFrames, int nR, const double*
                    const double* d_edge_table, double tol_phi, double tol_cos, unsigned int* d_counts,
                    long long* d_amb_idx, int amb_capacity, int* d_amb_count, void* stream);
 
+/* The same through host (pageable) buffers.  Builds np.histogramdd's edges itself; h_counts [nR][nbx][nby] receives
+ * the counts of every sample the two device passes could place, h_amb_idx[0 .. *h_n_amb) the flat ids (frame*nR + r)
+ * of the few that lie within the tie-break tolerance of a bin edge (to be binned by the caller with the reference's
+ * formula; spinrelax_b200/hist.py::_reference_bins is that formula). */
+int sr_sphere_hist_host(const float* h_vecs, long long nFrames, int nR, const double* h_q_rot, int nbx, int nby,
+                        unsigned int* h_counts, long long* h_amb_idx, int amb_capacity, int* h_n_amb);
+
 /* ------------------------------------------------------------------------------------------------
  * X-H bond vectors from Cartesian coordinates: the step in front of the hot path.
  * Replaces obtain_XHvecs(), calculate-Ct-from-traj.py:64-86: np.take(xyz, indexH, 1) - np.take(xyz, indexX, 1)

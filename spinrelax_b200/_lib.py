@@ -49,6 +49,7 @@ def _declare(lib):
         "sr_dq_hist3d": (i, [vp, ll, ll, vp, i, vp, vp, i, vp, vp]),
         "sr_vec_second_moments": (i, [vp, ll, i, vp, vp]),
         "sr_sphere_hist": (i, [vp, ll, i, dp, i, i, vp, _c.c_double, _c.c_double, vp, vp, i, vp, vp]),
+        "sr_sphere_hist_host": (i, [vp, ll, i, dp, i, i, vp, vp, i, vp]),
         "sr_xh_vectors": (i, [vp, ll, i, vp, vp, i, vp, vp]),
         "sr_xh_vectors_superposed": (i, [vp, ll, i, vp, vp, i, vp, vp, i, vp, vp, vp]),
     }

@@ -13,7 +13,9 @@
 //      with the reference's own NumPy formula; everything else in the list is overwritten with -1.
 #include "common.cuh"
 #include <algorithm>
+#include <cmath>
 #include <mutex>
+#include <vector>
 
 namespace {
 
@@ -327,4 +329,64 @@ extern "C" int sr_sphere_hist(const float* d_vecs, long long nFrames, int nR, co
                                                   d_amb_count, d_amb_start);
   SR_CUDA(cudaGetLastError());
   return SR_OK;
+}
+
+// Host-buffer entry point: builds NumPy's edges (np.linspace(-pi, pi, nbx + 1), np.linspace(-1, 1, nby + 1)) and the
+// edge-direction table itself, uploads the vectors, runs both passes and returns the counts plus the sample ids
+// the device left undecided (what a caller without NumPy cannot reproduce bit for bit is exactly that short list).
+extern "C" int sr_sphere_hist_host(const float* h_vecs, long long nFrames, int nR, const double* h_q_rot, int nbx, int nby,
+                                   unsigned int* h_counts, long long* h_amb_idx, int amb_capacity, int* h_n_amb) {
+  SR_REQUIRE(h_vecs && h_counts && h_amb_idx && h_n_amb, "sr_sphere_hist_host: null pointer");
+  SR_REQUIRE(nFrames > 0 && nR > 0 && nbx > 0 && nby > 0 && amb_capacity > 0, "sr_sphere_hist_host: empty shape");
+  const double kPi = 3.141592653589793;
+  std::vector<double> table((size_t)2 * (nbx + 1) + (nby + 1));
+  for (int i = 0; i <= nbx; ++i) {           // np.linspace: start + i * step, last point = stop
+    const double e = (i == nbx) ? kPi : -kPi + i * ((kPi - (-kPi)) / nbx);
+    table[2 * i] = cos(e); table[2 * i + 1] = sin(e);
+  }
+  for (int j = 0; j <= nby; ++j) table[2 * (nbx + 1) + j] = (j == nby) ? 1.0 : -1.0 + j * (2.0 / nby);
+  const size_t in_bytes = (size_t)nFrames * nR * 3 * sizeof(float);
+  const size_t cnt_bytes = (size_t)nR * nbx * nby * sizeof(unsigned int);
+  float* d_in = nullptr; double* d_table = nullptr; unsigned int* d_counts = nullptr; long long* d_amb = nullptr; int* d_namb = nullptr;
+  int rc = SR_OK;
+  cudaError_t e = cudaSuccess;
+  if ((e = cudaMalloc(&d_in, in_bytes)) != cudaSuccess || (e = cudaMalloc(&d_table, table.size() * sizeof(double))) != cudaSuccess ||
+      (e = cudaMalloc(&d_counts, cnt_bytes)) != cudaSuccess || (e = cudaMalloc(&d_amb, (size_t)amb_capacity * sizeof(long long))) != cudaSuccess ||
+      (e = cudaMalloc(&d_namb, sizeof(int))) != cudaSuccess ||
+      (e = cudaMemcpy(d_in, h_vecs, in_bytes, cudaMemcpyHostToDevice)) != cudaSuccess ||
+      (e = cudaMemcpy(d_table, table.data(), table.size() * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess ||
+      (e = cudaMemset(d_counts, 0, cnt_bytes)) != cudaSuccess || (e = cudaMemset(d_namb, 0, sizeof(int))) != cudaSuccess) {
+    sr_set_error("sr_sphere_hist_host: allocation / upload failed: %s", cudaGetErrorString(e));
+    rc = SR_ERR_CUDA;
+  }
+  // margins: FP64 resolve pass for the rotated stream; the reference's own float32 error for the unrotated one
+  const double tol_phi = h_q_rot ? 1e-11 : 4e-6, tol_cos = h_q_rot ? 1e-11 : 2e-6;
+  if (!rc) rc = sr_sphere_hist(d_in, nFrames, nR, h_q_rot, nbx, nby, d_table, tol_phi, tol_cos, d_counts, d_amb, amb_capacity,
+                               d_namb, nullptr);
+  int n = 0;
+  std::vector<long long> list;
+  if (!rc && ((e = cudaMemcpy(h_counts, d_counts, cnt_bytes, cudaMemcpyDeviceToHost)) != cudaSuccess ||
+              (e = cudaMemcpy(&n, d_namb, sizeof(int), cudaMemcpyDeviceToHost)) != cudaSuccess)) {
+    sr_set_error("sr_sphere_hist_host: download failed: %s", cudaGetErrorString(e));
+    rc = SR_ERR_CUDA;
+  }
+  if (!rc && n > amb_capacity) {
+    sr_set_error("sr_sphere_hist_host: %d retry samples exceed the list capacity %d", n, amb_capacity);
+    rc = SR_ERR_OVERFLOW;
+  }
+  if (!rc && n > 0) {
+    list.resize(n);
+    if ((e = cudaMemcpy(list.data(), d_amb, (size_t)n * sizeof(long long), cudaMemcpyDeviceToHost)) != cudaSuccess) {
+      sr_set_error("sr_sphere_hist_host: download failed: %s", cudaGetErrorString(e));
+      rc = SR_ERR_CUDA;
+    }
+  }
+  if (!rc) {
+    int k = 0;
+    for (int i = 0; i < n; ++i)
+      if (list[i] >= 0) h_amb_idx[k++] = list[i];      // -1 = resolved on the device
+    *h_n_amb = k;
+  }
+  cudaFree(d_in); cudaFree(d_table); cudaFree(d_counts); cudaFree(d_amb); cudaFree(d_namb);
+  return rc;
 }

@@ -104,3 +104,30 @@ def test_hist_accumulates_over_arrays():
         both = acc.finish(bd, rot)
         whole, _ = ct_oracle.sphere_histogram(np.concatenate((a, b)), rot)
         assert np.array_equal(both, whole.astype(np.int64))
+
+
+def test_hist_host_entry_point():
+    """sr_sphere_hist_host (C ABI on pageable host buffers): its counts plus its short undecided list, binned with the
+    reference formula, equal the oracle; the edges it builds itself are NumPy's."""
+    import ctypes
+    from spinrelax_b200 import _lib, hist, synth
+    lib = _lib.load()
+    for q in (np.array([0.83, -0.31, 0.22, 0.41]), None):
+        v = synth.nh_vectors(20011, 12, seed=21)
+        counts = np.zeros((12, 72, 36), dtype=np.uint32)
+        cap = 1 << 16
+        amb = np.zeros(cap, dtype=np.int64)
+        n_amb = ctypes.c_int(0)
+        qc = None if q is None else (ctypes.c_double * 4)(*q)
+        rc = lib.sr_sphere_hist_host(v.ctypes.data, v.shape[0], 12, qc, 72, 36, counts.ctypes.data, amb.ctypes.data, cap,
+                                     ctypes.byref(n_amb))
+        _lib.check(rc, "sr_sphere_hist_host")
+        total = counts.astype(np.int64).reshape(12, -1)
+        idx = amb[:n_amb.value]
+        if len(idx):
+            bins = hist._reference_bins(v.reshape(-1, 3)[idx], q, np.linspace(-np.pi, np.pi, 73), np.linspace(-1, 1, 37))
+            ok = bins >= 0
+            np.add.at(total, (idx[ok] % 12, bins[ok]), 1)
+        ho, _ = ct_oracle.sphere_histogram(v, q)
+        assert np.array_equal(total.reshape(12, 72, 36), ho.astype(np.int64))
+        assert n_amb.value < (50 if q is not None else 2000)
