@@ -317,16 +317,16 @@ using CtV10 = CtCfg<19, 6, 1, 12, 1, 3>;
 using CtV11 = CtCfg<17, 6, 2, 12, 1, 3>;
 using CtV12 = CtCfg<15, 8, 1, 8, 2, 3>;
 using CtV13 = CtCfg<19, 6, 3, 12, 1, 4>;
-using CtV14 = CtCfg<19, 3, 3, 12, 1, 4>;
+using CtV14 = CtCfg<19, 9, 3, 12, 1, 3>;
 using CtV15 = CtCfg<19, 6, 3, 12, 1, 3>;
-using CtV16 = CtCfg<17, 6, 3, 12, 1, 3>;
-using CtV17 = CtCfg<21, 6, 3, 12, 1, 3>;
+using CtV16 = CtCfg<19, 12, 3, 12, 1, 3>;
+using CtV17 = CtCfg<19, 12, 3, 12, 1, 2>;
 constexpr int kNumVariants = 18;
-constexpr int kLongVariant = 13;     // R = 19, 12 warps, 1 CTA/SM, 4 stages: 57 terms per FP32 partial sum
+constexpr int kLongVariant = 17;     // R = 19, 12 warps, 1 CTA/SM, 2 stages of 2736 frames: 57 terms per FP32 partial sum
 constexpr int kShortVariant = 12;    // R = 15, 8 warps, 2 CTAs/SM, 3 stages: 15 terms per FP32 partial sum (few chunk
                                      // means enter dCt when chunks are short, so keep its rounding at the 1e-7 level)
 constexpr long long kShortFrames = 8192;
-constexpr int kMaxTF = 1536, kMaxTL = 32 * 21;   // padding must cover the largest tile of any variant
+constexpr int kMaxTF = 2736, kMaxTL = 32 * 21;   // padding must cover the largest tile of any variant
 
 template <class Cfg>
 int launch_ct_lag(const float* U, long long pitch, long long nF, int nR, int nC, int c0, int nCsub, long long L, double* S,
