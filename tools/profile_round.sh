@@ -20,7 +20,7 @@ echo "ncu full pack rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:dq_moments -s 1 -c 1 -f -o gpurun_out/prof_dq_$TAG \
     python bench_secondary.py --quick > gpurun_out/ncu_full_dq_$TAG.log 2>&1
 echo "ncu full dq rc=$?"
-TUNE_VARIANTS=13 TUNE_NR=8 ncu --set full --clock-control none --import-source on -k regex:ct_lag -c 1 -f -o gpurun_out/prof_ctlag_slice_$TAG \
+TUNE_VARIANTS=17 TUNE_NR=8 ncu --set full --clock-control none --import-source on -k regex:ct_lag -c 1 -f -o gpurun_out/prof_ctlag_slice_$TAG \
     python tools/tune_ct.py > gpurun_out/ncu_full_ctlag_slice_$TAG.log 2>&1
 echo "ncu full ct_lag slice rc=$?"
 ls gpurun_out | grep $TAG
