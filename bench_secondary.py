@@ -103,10 +103,13 @@ def bench_fit_relax(quick):
     ac = fitct.autoCorrelations()
     ac.import_target_array([str(i) for i in range(nR)], [t] * nR, Y, SG)
     ac.fit_all_residues(fp=io.StringIO())                       # warm-up (module load, allocations)
+    fitct.KERNEL_EVENTS = []
     t0 = time.perf_counter()
     ac.fit_all_residues(fp=io.StringIO())
     torch.cuda.synchronize()
     fit_s = time.perf_counter() - t0
+    kern_ms = sum(a.elapsed_time(b) for a, b in fitct.KERNEL_EVENTS)
+    fitct.KERNEL_EVENTS = None
     t0 = time.perf_counter()
     nref = 8
     for i in range(nref):
@@ -115,6 +118,9 @@ def bench_fit_relax(quick):
     print(json.dumps({"metric": "ct_fit_residues_per_s", "value": nR / fit_s, "unit": "residues/s (full 2-3-5-7-9 ladder, "
                       "500-point curves, host selection logic included)", "n_gpus": 1, "ms_per_step": fit_s * 1e3,
                       "config": {"workload": "c5 fits: %d residues x 500-point C(t)" % nR}, "dtype": "f64",
+                      "kernel_ms": kern_ms, "kernel_only_residues_per_s": nR / (kern_ms * 1e-3),
+                      "note": "ct_fit_lm_kernel time summed over the five rungs; the rest of ms_per_step is the reference's "
+                              "per-residue selection ladder on the host (fitting_Ct_functions.py:278-304)",
                       "data": "synthetic", "roofline": None,
                       "cpu_baseline": {"value": cpu_fit, "unit": "residues/s", "cores": 1, "kind": "port",
                                        "sample": "oracle fit_ladder (SciPy curve_fit TRF, fitting_Ct_functions.py:278-345) on %d residues" % nref}}))

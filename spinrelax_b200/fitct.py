@@ -29,6 +29,9 @@ def curvefit_exponential(DeltaT, *params):
 
 
 # ---- GPU solve ----------------------------------------------------------------------------------------
+KERNEL_EVENTS = None      # set to a list to collect (start, end) CUDA event pairs around every sr_ct_fit_lm launch
+
+
 def gpu_curve_fit(t, y, sigma, p0, lo, hi):
     """Batched bounded least squares.  t, y, sigma: (nR, L) (sigma may be None); p0, lo, hi: (nR, nP).
     Returns popt (nR,nP), pcov (nR,nP,nP) formed like scipy.optimize.curve_fit (pinv of J^T J scaled by
@@ -47,22 +50,34 @@ def gpu_curve_fit(t, y, sigma, p0, lo, hi):
     JtJ = torch.empty((nR, nP, nP), dtype=torch.float64, device=dev)
     cost = torch.empty(nR, dtype=torch.float64, device=dev)
     status = torch.empty((nR, 2), dtype=torch.int32, device=dev)
+    if KERNEL_EVENTS is not None:
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
     _lib.check(lib.sr_ct_fit_lm(td.data_ptr(), yd.data_ptr(), 0 if sd is None else sd.data_ptr(), nR, L, nP,
                                 p0d.data_ptr(), lod.data_ptr(), hid.data_ptr(), MAX_ITER, FTOL, popt.data_ptr(),
                                 JtJ.data_ptr(), cost.data_ptr(), status.data_ptr(), _lib.current_stream_ptr()),
                "sr_ct_fit_lm")
+    if KERNEL_EVENTS is not None:
+        ev[1].record()
+        KERNEL_EVENTS.append(ev)
     popt, JtJ, cost, status = popt.cpu().numpy(), JtJ.cpu().numpy(), cost.cpu().numpy(), status.cpu().numpy()
-    pcov = np.zeros_like(JtJ)
-    for i in range(nR):
-        # scipy: SVD of J, drop singular values <= eps*max(M,n)*s0, pcov = V S^-2 V^T * 2 cost/(M-n)
-        w, V = np.linalg.eigh(JtJ[i])
-        s = np.sqrt(np.clip(w, 0.0, None))
-        keep = s > np.finfo(float).eps * max(L, nP) * s.max()
-        pc = (V[:, keep] / (s[keep] ** 2)) @ V[:, keep].T
-        if L > nP:
-            pcov[i] = pc * (2.0 * cost[i] / (L - nP))
-        else:
-            pcov[i] = np.inf
+    # scipy.optimize.curve_fit: SVD of J, drop singular values <= eps*max(M,n)*s0, pcov = V S^-2 V^T * 2 cost/(M-n);
+    # here from the eigen-decomposition of J^T J, batched over the residues
+    bad = ~np.all(np.isfinite(JtJ), axis=(1, 2))       # diverged fits: keep LAPACK away from NaNs, mark them below
+    if np.any(bad):
+        JtJ = JtJ.copy()
+        JtJ[bad] = 0.0
+    w, V = np.linalg.eigh(JtJ)
+    sv = np.sqrt(np.clip(w, 0.0, None))
+    keep = sv > (np.finfo(float).eps * max(L, nP)) * sv.max(axis=1, keepdims=True)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        inv = np.where(keep, 1.0 / (sv * sv), 0.0)
+    pcov = np.einsum("rik,rk,rjk->rij", V, inv, V)
+    if L > nP:
+        pcov *= (2.0 * cost / (L - nP))[:, None, None]
+    else:
+        pcov[:] = np.inf
+    pcov[bad] = np.nan
     return popt, pcov, cost, status
 
 
@@ -372,6 +387,114 @@ class autoCorrelations:
 
     # -- batched ladder: one kernel launch per rung for all residues still climbing --
     def fit_all_residues(self, listDoG=(2, 3, 5, 7, 9), chiSqThreshold=0.5, fp=sys.stdout, single=False):
+        """calculate-fitted-Ct.py:162-178 for every target at once: one kernel launch per rung for all residues still
+        climbing the ladder, and the reference's per-residue bookkeeping (initial guesses :359-374, quality flags and
+        chi^2 :329-345, selection :278-304) evaluated as array operations over those residues.  Adds/overwrites one
+        model per target key.  `fit_all_residues_loop` is the same ladder residue by residue through the model
+        objects (kept as the specification; the two are tested to agree exactly)."""
+        keys = list(self.DeltaT.keys())
+        if single or len({len(self.DeltaT[k]) for k in keys}) != 1:
+            return self.fit_all_residues_loop(listDoG, chiSqThreshold, fp, single)
+        n = len(keys)
+        T = np.array([self.DeltaT[k] for k in keys], dtype=float)
+        Y = np.array([self.Decay[k] for k in keys], dtype=float)
+        has_sig = self.dDecay[keys[0]] is not None
+        SG = np.array([self.dDecay[k] for k in keys], dtype=float) if has_sig else None
+        work = {k: self.model[k] if k in self.model else self.add_model(k, name=_as_name(k)) for k in keys}
+        zeta = np.array([work[k].zeta for k in keys], dtype=float)
+        names = [work[k].name for k in keys]
+        dtm = np.mean(T[:, 1:] - T[:, :-1], axis=1)                  # initialise_for_fit_advanced (:365-373)
+        avgBeg, avgEnd = np.mean(Y[:, :10], axis=1), np.mean(Y[:, -10:], axis=1)
+        first = np.ones(n, dtype=bool)
+        maxc = max(int(p / 2) for p in listDoG)
+        best = dict(nParams=np.zeros(n, dtype=int), C=np.zeros((n, maxc)), tau=np.zeros((n, maxc)), S2=np.zeros(n),
+                    dC=np.zeros((n, maxc)), dtau=np.zeros((n, maxc)), dS2=np.zeros(n), chi=np.full(n, np.inf),
+                    fit=np.zeros(n, dtype=bool))
+        last = {key: val.copy() for key, val in best.items()}        # state of the last rung tried (for residues never accepted)
+        active = np.arange(n)
+        lines = []
+        for nParams in listDoG:
+            if active.size == 0:
+                break
+            a = active
+            nc, fast = int(nParams / 2), (nParams % 2 == 1)
+            tau0 = np.power(10.0, np.linspace(np.log10(dtm[a]), np.log10(T[a, -1] * 2.0), nc + 2, axis=-1))[:, 1:-1]
+            C0 = np.repeat((np.fabs(avgBeg[a] - avgEnd[a]) / nc)[:, None], nc, axis=1)
+            S20 = avgEnd[a] if fast else 1.0 - np.mean(C0, axis=1)
+            p0 = np.concatenate((C0, tau0) + ((S20[:, None],) if fast else ()), axis=1)
+            hi = np.concatenate((np.ones((a.size, nc)), np.repeat((T[a, -1] * 10)[:, None], nc, axis=1)) +
+                                ((np.ones((a.size, 1)),) if fast else ()), axis=1)
+            popt, pcov, cost, status = gpu_curve_fit(T[a], Y[a], None if SG is None else SG[a], p0, np.zeros_like(p0), hi)
+            finite = np.all(np.isfinite(popt), axis=1)
+            with np.errstate(invalid="ignore"):
+                dParam = np.sqrt(np.diagonal(pcov, axis1=1, axis2=2))
+                # quality flags as conduct_curve_fitting raises them, i.e. on the initial-guess state (:329-337, quirk G6)
+                sumC0 = np.sum(C0, axis=1)
+                S2_state = S20 if fast else 1.0 - sumC0
+                q_over = ~np.any(dParam > popt, axis=1)
+                q_sum = ~((S2_state + sumC0) > 1.0)
+                C, tau = popt[:, :nc], popt[:, nc:2 * nc]
+                S2 = popt[:, -1] if fast else 1.0 - np.sum(C, axis=1)
+                model = zeta[a][:, None] * (S2[:, None] + np.sum(C[:, :, None] * np.exp(-1.0 * T[a][:, None, :] / tau[:, :, None]),
+                                                                  axis=1))
+                chi = np.mean(np.square(model - Y[a]), axis=1) if SG is None else np.mean(np.square(model - Y[a]) / SG[a], axis=1)
+            chi = np.where(finite, chi, np.inf)
+            q_over, q_sum = np.where(finite, q_over, True), np.where(finite, q_sum, True)
+            ok = finite & q_over & q_sum
+            order = np.argsort(tau, axis=1)                           # sort_components
+            take = lambda x: np.take_along_axis(x, order, axis=1)     # noqa: E731
+            Cs, taus = take(C), take(tau)
+            dCs, dtaus = take(dParam[:, :nc]), take(dParam[:, nc:2 * nc])
+            dS2 = dParam[:, -1] if fast else np.zeros(a.size)
+            for j, i in enumerate(a):
+                if finite[j]:
+                    if not q_over[j]:
+                        lines.append("= = = WARNING, curve fitting of %s with %i params indicates overfitting." % (names[i], nParams))
+                    if not q_sum[j]:
+                        lines.append("= = = WARNING, curve fitting of %s with %i params returns sum>1." % (names[i], nParams))
+                lines.append("    ...%s: fit with %i params yield chiSq of %g" % (names[i], nParams, chi[j]))
+            # selection ladder (optimised_curve_fitting :288-304)
+            was_first = first[a]
+            accept = np.where(was_first, ok, ok & ~(chi >= best["chi"][a] * chiSqThreshold))
+            still = was_first | accept
+            first[a[was_first & ok]] = False
+
+            def store(dst, rows, sel):
+                dst["nParams"][rows] = nParams
+                dst["C"][rows, :nc], dst["tau"][rows, :nc] = Cs[sel], taus[sel]
+                dst["dC"][rows, :nc], dst["dtau"][rows, :nc] = dCs[sel], dtaus[sel]
+                dst["S2"][rows], dst["dS2"][rows], dst["chi"][rows], dst["fit"][rows] = S2[sel], dS2[sel], chi[sel], True
+
+            store(best, a[accept], accept)
+            # residues that have never produced an acceptable fit keep the state of their latest attempt
+            pend = first[a]
+            got = pend & finite
+            store(last, a[got], got)
+            miss = pend & ~finite
+            if np.any(miss):                                          # failed fit: the model stays at its initial guess
+                rows = a[miss]
+                last["nParams"][rows], last["fit"][rows] = nParams, False
+                last["C"][rows, :nc], last["tau"][rows, :nc], last["S2"][rows] = C0[miss], tau0[miss], S20[miss]
+            active = a[still]
+        if lines:
+            print("\n".join(lines), file=fp)
+        out = np.full(n, np.inf)
+        for i, k in enumerate(keys):
+            src = last if first[i] else best
+            if first[i]:
+                print("    ...ERROR: fit of %s has never generated a satisfactory outcome!" % str(k), file=fp)
+            m, nc = work[k], int(src["nParams"][i] / 2)
+            m.set_nParams(int(src["nParams"][i]))
+            m.C, m.tau, m.S2 = src["C"][i, :nc].copy(), src["tau"][i, :nc].copy(), float(src["S2"][i])
+            m.bHasFit = bool(src["fit"][i])
+            if m.bHasFit:
+                m.dC, m.dtau = src["dC"][i, :nc].copy(), src["dtau"][i, :nc].copy()
+                m.dS2 = float(src["dS2"][i]) if m.bS2Fast else 0.0
+                m.chiSq = float(src["chi"][i])
+                out[i] = m.chiSq
+        return out
+
+    def fit_all_residues_loop(self, listDoG=(2, 3, 5, 7, 9), chiSqThreshold=0.5, fp=sys.stdout, single=False):
         """calculate-fitted-Ct.py:162-178 for every target at once.  Adds/overwrites one model per target key.
         single=True reproduces the fixed-parameter-count branch (:174-178): one conduct_curve_fitting per residue,
         result kept whatever its quality flags."""

@@ -1,5 +1,6 @@
 """GPU parity of K5 (batched C(t) fits), K6 (J(omega) -> R1/R2/NOE) and K7 (Jomega ufunc)."""
 import io
+import os
 
 import numpy as np
 import pytest
@@ -290,3 +291,34 @@ def test_cli_relax_optimisation_matches_reference(golden, tmp_path, mode):
             csa, csa_ref = np.loadtxt(pref + "_CSA_opt.dat"), g["csa_" + mode]
             assert np.array_equal(csa[:, 0], csa_ref[:, 0])
             assert np.max(np.abs(csa[:, 1] / csa_ref[:, 1] - 1)) < (2e-4 if local == "powell" else 3e-3)
+
+
+def test_vectorised_ladder_equals_residue_loop(golden):
+    """fit_all_residues (array form of the selection ladder) against fit_all_residues_loop (the reference's
+    per-residue flow through the model objects): same rung chosen, same parameters, same printed log lines."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+    from bench_secondary import synth_curves
+    from spinrelax_b200 import fitct
+    f = golden("fit.npz")
+    sets = [synth_curves(60, 500, 77), (f["t"], f["Ct"], f["dCt"])]
+    for t, Y, SG in sets:
+        nR = len(Y)
+        for sig in (SG, None):
+            res = []
+            for method in ("fit_all_residues", "fit_all_residues_loop"):
+                ac = fitct.autoCorrelations()
+                ac.import_target_array([str(i) for i in range(nR)], [t] * nR, Y, sig)
+                log = io.StringIO()
+                chis = getattr(ac, method)(fp=log)
+                res.append((ac, chis, sorted(log.getvalue().splitlines())))
+            (a, ca, la), (b, cb, lb) = res
+            assert np.array_equal(ca, cb)
+            assert la == lb
+            for k in a.model:
+                ma, mb = a.model[k], b.model[k]
+                assert (ma.nParams, ma.bS2Fast, ma.bHasFit) == (mb.nParams, mb.bS2Fast, mb.bHasFit), k
+                assert np.array_equal(ma.C, mb.C) and np.array_equal(ma.tau, mb.tau) and ma.S2 == mb.S2, k
+                if ma.bHasFit:
+                    assert np.allclose(ma.dC, mb.dC, rtol=1e-9, atol=0) and np.allclose(ma.dtau, mb.dtau, rtol=1e-9, atol=0)
+                    assert ma.chiSq == mb.chiSq
