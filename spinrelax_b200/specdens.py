@@ -203,6 +203,10 @@ class globalRotationalDiffusion_Base:
         """vecs (nR, B, 3), weights (nR, B): stored swapped to (B, nR, ...) like the reference (:302-306)."""
         self.bVecs = True
         self.vecNames = names
+        vecs = np.asarray(vecs)
+        # histogram-derived distributions use the same bin vectors for every residue (:2349): the A_J coefficients
+        # are then needed once, not per residue
+        self._shared_bins = bool(vecs.shape[0] > 0 and np.array_equal(vecs, np.broadcast_to(vecs[:1], vecs.shape)))
         self.vecXH = np.swapaxes(vecs, 0, 1)
         self.vecWeights = np.swapaxes(weights, 0, 1)
         self.axisAvg = 0
@@ -325,12 +329,16 @@ class globalRotationalDiffusion_Axisymmetric(globalRotationalDiffusion_Base):
         if getattr(self, "_amom", None) is None:
             torch = _lib.require_cuda()
             lib = _lib.load()
-            A = np.ascontiguousarray(np.swapaxes(self.A_J, 0, 1), dtype=np.float64)          # (nR, B, 3)
-            W = np.ascontiguousarray(np.swapaxes(self.vecWeights, 0, 1), dtype=np.float64)  # (nR, B)
+            shared = getattr(self, "_shared_bins", False)
+            if shared:
+                A = np.ascontiguousarray(self.A_J[:, 0, :], dtype=np.float64)                    # (B, 3)
+            else:
+                A = np.ascontiguousarray(np.swapaxes(self.A_J, 0, 1), dtype=np.float64)          # (nR, B, 3)
+            W = np.ascontiguousarray(np.swapaxes(self.vecWeights, 0, 1), dtype=np.float64)      # (nR, B)
             Ad, Wd = torch.from_numpy(A).cuda(), torch.from_numpy(W).cuda()
-            out = torch.empty((A.shape[0], 10), dtype=torch.float64, device=Ad.device)
-            _lib.check(lib.sr_relax_a_moments(Ad.data_ptr(), 1, Wd.data_ptr(), A.shape[0], A.shape[1], out.data_ptr(),
-                                              _lib.current_stream_ptr()), "sr_relax_a_moments")
+            out = torch.empty((W.shape[0], 10), dtype=torch.float64, device=Ad.device)
+            _lib.check(lib.sr_relax_a_moments(Ad.data_ptr(), 0 if shared else 1, Wd.data_ptr(), W.shape[0], W.shape[1],
+                                              out.data_ptr(), _lib.current_stream_ptr()), "sr_relax_a_moments")
             self._amom = out
         return self._amom
 
