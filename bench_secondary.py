@@ -158,12 +158,42 @@ def bench_fit_relax(quick):
                                                  "on %d residues, 1 field, 1 CSA" % nref}}))
 
 
+def bench_rtp():
+    """--vecDist spherical conversion on the config-2 stream (25.6M float32 vectors): HBM-bound, 24 B/vector."""
+    import torch
+    from oracle import ct_oracle
+    from spinrelax_b200 import gm, synth
+    nF, nR = 100000, 256
+    v = synth.nh_vectors(nF, nR, seed=synth.BASE_SEED + 2)
+    vd = torch.from_numpy(v).cuda()
+    ms = ev_ms(torch, lambda: gm.xyz_to_rtp_device(vd), reps=5)
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    n = nF * nR
+    sub = v[:4000]
+    t0 = time.perf_counter()
+    ct_oracle.xyz_to_rtp(sub)
+    cpu = sub.shape[0] * nR / (time.perf_counter() - t0)
+    print(json.dumps({"metric": "rtp_vectors_per_s", "value": n / ms * 1e3, "unit": "vectors/s", "n_gpus": 1,
+                      "ms_per_step": ms, "config": {"workload": "c2 stream: gm.xyz_to_rtp on (100000, 256, 3) float32"},
+                      "dtype": "f32", "data": "synthetic",
+                      "roofline": {"kernel": "xyz_to_rtp_vec4_kernel<float>", "bound": "hbm", "achieved": n * 24 / ms * 1e-6,
+                                   "unit": "GB/s", "peak": peak, "frac": n * 24 / ms * 1e-6 / peak},
+                      "cpu_baseline": {"value": cpu, "unit": "vectors/s", "cores": 1, "kind": "port",
+                                       "sample": "oracle xyz_to_rtp (general_maths.py:143-158) on 4000 frames x 256"}}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--only", default="", help="dq | fit | rtp")
     args = ap.parse_args()
-    bench_dq(args.quick)
-    bench_fit_relax(args.quick)
+    if args.only in ("", "dq"):
+        bench_dq(args.quick)
+    if args.only in ("", "fit"):
+        bench_fit_relax(args.quick)
+    if args.only in ("", "rtp"):
+        bench_rtp()
 
 
 if __name__ == "__main__":

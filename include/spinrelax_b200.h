@@ -152,6 +152,14 @@ int sr_vec_block_moments(const float* d_vecs, long long nFrames, int nR, long lo
  * to NumPy (separately rounded products/sums in NumPy's order). */
 int sr_rotate_vectors_f32_f64(const float* d_v, long long n, const double* h_q, double* d_out, void* stream);
 
+/* gm.xyz_to_rtp(uv, vaxis=-1, bUnit) (general_maths.py:118-158) for n vectors stored (n,3), computed in the
+ * precision of the input as NumPy does.  unit_form == 0: d_out (n,3) = (|v|, atan2(y,x), acos(z/|v|)), |v|
+ * bit-identical to np.linalg.norm(uv, axis=-1).  unit_form != 0: d_out (n,2) = (phi, acos(z/phi)), the shipped
+ * bUnit branch (:131-133 divides by phi).  Called on (frames, nR, 3) by calculate-Ct-from-traj.py:588 for the
+ * _vecPhiTheta.{npz,dat} outputs; phi/theta agree with libm to <= 2 ulp. */
+int sr_xyz_to_rtp_f32(const float* d_v, long long n, float* d_out, int unit_form, void* stream);
+int sr_xyz_to_rtp_f64(const double* d_v, long long n, double* d_out, int unit_form, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * K4: quaternion-displacement statistics over lag windows.
  * Replaces the per-lag body of calculate-dq-distribution.py:554-625: obtain_self_dq (:102-109),

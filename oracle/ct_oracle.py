@@ -100,13 +100,25 @@ def rotate_vectors(v, q):
     return b + b + v
 
 
-def xyz_to_rtp(uv):
-    """gm.xyz_to_rtp(uv) for the last-axis case, general_maths.py:143-158."""
+def xyz_to_rtp(uv, bUnit=False):
+    """gm.xyz_to_rtp(uv) for the last-axis case, general_maths.py:143-158; bUnit: :131-133 (divides by phi)."""
+    if bUnit:
+        out = np.zeros(uv.shape[:-1] + (2,), dtype=uv.dtype)
+        out[..., 0] = np.arctan2(uv[..., 1], uv[..., 0])
+        out[..., 1] = np.arccos(uv[..., 2] / out[..., 0])
+        return out
     out = np.zeros_like(uv)
     out[..., 0] = np.linalg.norm(uv, axis=-1)
     out[..., 1] = np.arctan2(uv[..., 1], uv[..., 0])
     out[..., 2] = np.arccos(uv[..., 2] / out[..., 0])
     return out
+
+
+def spherical_by_residue(frames_vecs, q_rot=None):
+    """--vecDist without --vecHist (calculate-Ct-from-traj.py:567,588,600): (nR, frames, 3) r/phi/theta."""
+    w = rotate_vectors(frames_vecs, q_rot) if q_rot is not None else frames_vecs
+    with np.errstate(all="ignore"):
+        return np.transpose(xyz_to_rtp(w), axes=(1, 0, 2))
 
 
 def sphere_histogram(frames_vecs, q_rot=None, nbins_phi=72):

@@ -37,6 +37,8 @@ def _declare(lib):
         "sr_sphere_hist_table_doubles": (i, [i, i]),
         "sr_vec_block_moments": (i, [vp, ll, i, ll, vp, vp]),
         "sr_rotate_vectors_f32_f64": (i, [vp, ll, dp, vp, vp]),
+        "sr_xyz_to_rtp_f32": (i, [vp, ll, vp, i, vp]),
+        "sr_xyz_to_rtp_f64": (i, [vp, ll, vp, i, vp]),
         "sr_jomega_f64": (i, [vp, vp, vp, ll, vp]),
         "sr_jomega_f32": (i, [vp, vp, vp, ll, vp]),
         "sr_relax_a_moments": (i, [vp, i, vp, i, i, vp, vp]),

@@ -107,6 +107,24 @@ def _load(fn, ref_fn=None):
     sys.exit(2)
 
 
+def _spherical_by_residue(frames, q_rot=None):
+    """(frames, nR, 3) float32 -> (nR, frames, 3) r/phi/theta as calculate-Ct-from-traj.py:567,588,600 produce it:
+    float32 without --vecRot, float64 after the PAF rotation (rotate_vector_simd promotes)."""
+    import ctypes
+    from . import _lib, gm, qs
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    vd = torch.from_numpy(np.ascontiguousarray(frames, dtype=np.float32)).cuda()
+    if q_rot is not None:
+        q = qs.vecnorm_NDarray(np.asarray(q_rot, dtype=np.float64))
+        rot = torch.empty(vd.shape, dtype=torch.float64, device=vd.device)
+        _lib.check(lib.sr_rotate_vectors_f32_f64(vd.data_ptr(), vd.numel() // 3, (ctypes.c_double * 4)(*q.tolist()),
+                                                 rot.data_ptr(), _lib.current_stream_ptr()), "sr_rotate_vectors_f32_f64")
+        vd = rot
+    rtp = gm.xyz_to_rtp_device(vd)
+    return rtp.permute(1, 0, 2).contiguous().cpu().numpy()
+
+
 def main(argv=None):
     args = build_parser().parse_args(argv)
     time_start = time.time()
@@ -186,9 +204,16 @@ def main(argv=None):
 
     if bDoVecDistrib:
         if not args.bDoVecHist:
-            print("= = = ERROR: only the histogram form of the vector distribution (--vecHist) is produced on this path.",
-                  file=sys.stderr)
-            sys.exit(2)
+            # calculate-Ct-from-traj.py:586-607: spherical coordinates of every sample, residue first
+            print("= = = Converting vectors into spherical coordinates.")
+            rtp = _spherical_by_residue(frames, q_rot)
+            print("= = = Debug: shape of the spherical vector distribution:", rtp.shape)
+            if args.binary:
+                np.savez_compressed(args.out_pref + '_vecPhiTheta.npz', names=resXH, dataType='PhiTheta',
+                                    axisLabels=['phi', 'theta'], bHistogram=False, data=rtp[..., 1:3])
+            else:
+                io_formats.print_s3d(args.out_pref + '_vecPhiTheta.dat', resXH, rtp, (1, 2))
+    if args.bDoVecHist:
         print("= = = Histgrams will use Lambert Cylindrical projection by converting Theta spanning (0,pi) to "
               "cos(Theta) spanning (-1,1)")
         hist_list, edges = hist.sphere_histogram(frames, q_rot, histBinX)

@@ -93,3 +93,115 @@ extern "C" int sr_vec_block_moments(const float* d_vecs, long long nFrames, int 
   SR_CUDA(cudaGetLastError());
   return SR_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// gm.xyz_to_rtp (general_maths.py:118-158), last-axis layout, in the precision of the input like NumPy:
+//   full form  (r, phi, theta) = (|v|, atan2(y, x), acos(z / r)); |v| = sqrt((x*x + y*y) + z*z) with every
+//              operation rounded separately (np.linalg.norm over an axis of length 3) -> r is bit-identical;
+//   bUnit form (phi, acos(z / phi)) -- the reference divides by phi there (:131-133) and so does this.
+// phi / theta differ from glibc / SVML by the last ulp or two (CUDA atan2/acos are <= 2 ulp), never more.
+// ------------------------------------------------------------------------------------------------
+namespace {
+__device__ __forceinline__ float sr_mul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double sr_mul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float sr_add(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double sr_add(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ float sr_sqrt(float a) { return __fsqrt_rn(a); }
+__device__ __forceinline__ double sr_sqrt(double a) { return __dsqrt_rn(a); }
+__device__ __forceinline__ float sr_div(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ double sr_div(double a, double b) { return __ddiv_rn(a, b); }
+__device__ __forceinline__ float sr_atan2(float y, float x) { return atan2f(y, x); }
+__device__ __forceinline__ double sr_atan2(double y, double x) { return atan2(y, x); }
+__device__ __forceinline__ float sr_acos(float a) { return acosf(a); }
+__device__ __forceinline__ double sr_acos(double a) { return acos(a); }
+
+template <typename T>
+__device__ __forceinline__ void rtp_one(T x, T y, T z, int unitForm, T& r, T& phi, T& theta) {
+  phi = sr_atan2(y, x);
+  if (unitForm) {
+    r = phi;
+    theta = sr_acos(sr_div(z, phi));
+  } else {
+    r = sr_sqrt(sr_add(sr_add(sr_mul(x, x), sr_mul(y, y)), sr_mul(z, z)));
+    theta = sr_acos(sr_div(z, r));
+  }
+}
+
+// Main kernel: a thread owns 4 consecutive vectors = 12 values, moved as 16-byte loads / stores straight from and
+// to registers (3 x LDG.128 for float, 6 for double); 48-96 B in flight per thread keeps HBM busy without staging.
+template <typename T>
+__global__ void __launch_bounds__(256)
+xyz_to_rtp_vec4_kernel(const T* __restrict__ v, long long nGroups, T* __restrict__ out, int unitForm) {
+  constexpr int kPer16 = 16 / (int)sizeof(T);            // values per 16-byte chunk
+  constexpr int kIn = 12 / kPer16;                       // chunks in, 3 or 6
+  const long long g = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (g >= nGroups) return;
+  union { int4 q[kIn]; T s[12]; } in, res;
+  const int4* src = reinterpret_cast<const int4*>(v + g * 12);
+#pragma unroll
+  for (int k = 0; k < kIn; ++k) in.q[k] = __ldg(src + k);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    T r, phi, theta;
+    rtp_one<T>(in.s[3 * k], in.s[3 * k + 1], in.s[3 * k + 2], unitForm, r, phi, theta);
+    if (unitForm) {
+      res.s[2 * k] = phi; res.s[2 * k + 1] = theta;
+    } else {
+      res.s[3 * k] = r; res.s[3 * k + 1] = phi; res.s[3 * k + 2] = theta;
+    }
+  }
+  if (unitForm) {
+    int4* dst = reinterpret_cast<int4*>(out + g * 8);
+#pragma unroll
+    for (int k = 0; k < 8 / kPer16; ++k) dst[k] = res.q[k];
+  } else {
+    int4* dst = reinterpret_cast<int4*>(out + g * 12);
+#pragma unroll
+    for (int k = 0; k < kIn; ++k) dst[k] = res.q[k];
+  }
+}
+
+// Tail (< 4 vectors) and unaligned buffers: one vector per thread.
+template <typename T>
+__global__ void __launch_bounds__(256)
+xyz_to_rtp_scalar_kernel(const T* __restrict__ v, long long first, long long n, T* __restrict__ out, int unitForm) {
+  const long long i = first + (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  T r, phi, theta;
+  rtp_one<T>(v[3 * i], v[3 * i + 1], v[3 * i + 2], unitForm, r, phi, theta);
+  if (unitForm) {
+    out[2 * i] = phi; out[2 * i + 1] = theta;
+  } else {
+    out[3 * i] = r; out[3 * i + 1] = phi; out[3 * i + 2] = theta;
+  }
+}
+
+template <typename T>
+int xyz_to_rtp_launch(const T* d_v, long long n, T* d_out, int unitForm, void* stream) {
+  SR_REQUIRE(d_v && d_out, "sr_xyz_to_rtp: null pointer");
+  SR_REQUIRE(n >= 1, "sr_xyz_to_rtp: empty input");
+  SR_REQUIRE(n / 1024 + 1 <= 2147483647LL, "sr_xyz_to_rtp: too many vectors");
+  const bool aligned = ((uintptr_t)d_v % 16 == 0) && ((uintptr_t)d_out % 16 == 0);
+  const long long nGroups = aligned ? n / 4 : 0;
+  if (nGroups > 0) {
+    xyz_to_rtp_vec4_kernel<T><<<(unsigned)((nGroups + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_v, nGroups, d_out,
+                                                                                                  unitForm);
+    SR_CUDA(cudaGetLastError());
+  }
+  const long long rest = n - nGroups * 4;
+  if (rest > 0) {
+    SR_REQUIRE((rest + 255) / 256 <= 2147483647LL, "sr_xyz_to_rtp: too many vectors");
+    xyz_to_rtp_scalar_kernel<T><<<(unsigned)((rest + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_v, nGroups * 4, n,
+                                                                                                 d_out, unitForm);
+    SR_CUDA(cudaGetLastError());
+  }
+  return SR_OK;
+}
+}  // namespace
+
+extern "C" int sr_xyz_to_rtp_f32(const float* d_v, long long n, float* d_out, int unit_form, void* stream) {
+  return xyz_to_rtp_launch<float>(d_v, n, d_out, unit_form, stream);
+}
+extern "C" int sr_xyz_to_rtp_f64(const double* d_v, long long n, double* d_out, int unit_form, void* stream) {
+  return xyz_to_rtp_launch<double>(d_v, n, d_out, unit_form, stream);
+}

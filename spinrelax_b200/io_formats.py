@@ -84,6 +84,25 @@ def print_sxylist(fn, legend, x, ylist, header=[]):
             print("&", file=fp)
 
 
+def print_s3d(fn, legend, arr, cols, header=[]):
+    """gs.print_s3d (general_scripts.py:292-307): one xmgrace set per arr[i], rows of "%g" of the chosen columns.
+    The shipped loop reuses its set counter for the row string and stops with a TypeError after the first set;
+    this writes every set, numbered as the first one is there.  Rows are formatted a set at a time."""
+    arr = np.asarray(arr)
+    cols = list(cols)
+    fmt = " ".join(["%g"] * len(cols))
+    with open(fn, 'w') as fp:
+        for line in header:
+            print("%s" % line, file=fp)
+        for s in range(arr.shape[0]):
+            print("@s%d legend \"%s\"" % (s, legend[s]), file=fp)
+            block = arr[s][:, cols]
+            if len(block):
+                fp.write("\n".join(fmt % tuple(row) for row in block.tolist()))
+                fp.write("\n")
+            print("&", file=fp)
+
+
 def load_sxydylist(fn, key="legend"):
     """Reads xmgrace sets `x y [dy]` separated by `&`; returns legends, x, y, dy arrays (dy=[] when absent)."""
     legs, xs, ys, dys = [], [], [], []

@@ -145,6 +145,42 @@ def golden_hist(refct):
     save("s2.npz", vecs=vr[:5000], s2_blocks=s2, s2_all=s2_all)
 
 
+def golden_rtp():
+    """The REAL gm.xyz_to_rtp / gm.rtp_to_xyz and qs.rotate_vector_simd on the --vecDist (no --vecHist) branch
+    (calculate-Ct-from-traj.py:567,588,600-607): float32 without rotation, float64 after it."""
+    qs = ref_loader.module("transforms3d_supplement")
+    gm = ref_loader.module("general_maths")
+    q = np.array([0.83, -0.31, 0.22, 0.41])
+    q = q / np.linalg.norm(q)
+    v = synth.nh_vectors(700, 5, seed=synth.BASE_SEED + 31)
+    v[:3] *= np.float32(1.7)                                   # non-unit rows: r is a real output
+    v[5, :, :] = 0
+    v[5, 0, 2] = 1; v[5, 1, 2] = -1; v[5, 2, 0] = -1; v[5, 3, 1] = -1       # poles, branch cut, zero vector
+    with np.errstate(all="ignore"):
+        rtp32 = gm.xyz_to_rtp(v)
+        rtp64 = gm.xyz_to_rtp(qs.rotate_vector_simd(v, q))
+        unit64 = gm.xyz_to_rtp(v.astype(np.float64), bUnit=True)
+        ax0 = gm.xyz_to_rtp(np.ascontiguousarray(np.moveaxis(v[:9].astype(np.float64), -1, 0)), vaxis=0)
+        one = gm.xyz_to_rtp(v[7, 2].astype(np.float64))
+    pt = np.stack(np.meshgrid(np.linspace(-3, 3, 7), np.linspace(0.1, 3.0, 5), indexing="ij"), axis=-1)
+    back = gm.rtp_to_xyz(pt, vaxis=-1, bUnit=True)
+    back1 = gm.rtp_to_xyz(np.array([1.3, 0.4, 2.1]))
+    # gs.print_s3d stops with a TypeError after its first set (general_scripts.py:303-306): keep what it wrote
+    import gc
+    import tempfile
+    gs = ref_loader.module("general_scripts")
+    with tempfile.TemporaryDirectory() as td:
+        try:
+            gs.print_s3d(td + "/pt.dat", ["A", "B", "C", "D", "E"], np.transpose(rtp64, axes=(1, 0, 2)), (1, 2))
+            crashed = False
+        except TypeError:
+            crashed = True
+        gc.collect()
+        s3d = open(td + "/pt.dat").read()
+    save("rtp.npz", s3d_partial=np.array(s3d), s3d_crashed=np.array(crashed), q=q, vecs=v, rtp32=rtp32, rtp64=rtp64, unit64=unit64, ax0=ax0, one=one, pt=pt, back=back,
+         back1=back1)
+
+
 def golden_dq(refdq):
     q = synth.quaternion_walk(6000, seed=synth.BASE_SEED + 31, sigma=(0.01, 0.015, 0.03))     # float32 (G2)
     lags = [5, 10, 40, 100, 333, 1000, 2999]
@@ -427,11 +463,16 @@ def golden_relax_opt():
 def main():
     if not ref_loader.available():
         sys.exit("reference tree not found at %s" % ref_loader.REFERENCE)
+    if len(sys.argv) > 1:                       # regenerate selected files only: make_golden.py golden_rtp ...
+        for name in sys.argv[1:]:
+            globals()[name]()
+        return
     refct = ref_loader.script("calculate-Ct-from-traj.py")
     refdq = ref_loader.script("calculate-dq-distribution.py")
     golden_ct(refct)
     golden_traj(refct)
     golden_hist(refct)
+    golden_rtp()
     golden_dq(refdq)
     golden_dq_multi(refdq)
     golden_fit()

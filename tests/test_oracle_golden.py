@@ -210,3 +210,27 @@ def test_dq_pooled_and_hist3d_match_reference(golden):
         idx = g["hist_%d_idx" % d]
         assert np.array_equal(np.stack(np.nonzero(h), axis=1), idx)
         assert np.array_equal(h[tuple(idx.T)], g["hist_%d_val" % d])
+
+
+def _ulps(a, b):
+    """|a-b| in units of the spacing at b; NaNs must coincide."""
+    a, b = np.asarray(a), np.asarray(b)
+    assert np.array_equal(np.isnan(a), np.isnan(b))
+    ok = ~np.isnan(b)
+    with np.errstate(all="ignore"):
+        return np.max(np.abs(a[ok] - b[ok]) / np.spacing(np.abs(b[ok]))) if ok.any() else 0.0
+
+
+def test_spherical_coordinates_match_reference(golden):
+    """--vecDist without --vecHist: gm.xyz_to_rtp in float32 and (after rotation) float64, and the bUnit form."""
+    g = golden("rtp.npz")
+    with np.errstate(all="ignore"):
+        r32 = ct_oracle.xyz_to_rtp(g["vecs"])
+        u64 = ct_oracle.xyz_to_rtp(g["vecs"].astype(np.float64), bUnit=True)
+    assert r32.dtype == np.float32 and np.array_equal(r32[..., 0], g["rtp32"][..., 0])
+    assert _ulps(r32, g["rtp32"]) <= 2 and _ulps(u64, g["unit64"]) <= 2
+    byres = ct_oracle.spherical_by_residue(g["vecs"], g["q"])
+    assert byres.dtype == np.float64 and byres.shape == (5, 700, 3)
+    assert _ulps(byres, np.transpose(g["rtp64"], (1, 0, 2))) <= 2
+    # the shipped text writer stops after its first set; what it wrote is the head of the complete file
+    assert bool(g["s3d_crashed"])
