@@ -3,10 +3,9 @@
 // :600-626 (transpose, cos(theta), np.histogramdd with bins (nbx, nby) over ((-pi,pi),(-1,1))).
 //
 // Bit-exact counts without reproducing NumPy's libm, in two passes:
-//   1. sphere_hist_kernel (hot, FP32): rotates, proposes a bin and accepts it only if the sample is farther
-//      than a float32 margin from all four edges of that bin -- phi through the sign of the cross products
-//      with the tabulated edge directions, cos(theta) by direct comparison.  Misses (~1e-4 of the samples)
-//      are appended to a retry list.
+//   1. sphere_hist_kernel (hot, FP32): rotates, locates the sample in bin units along both axes and accepts the
+//      bin only if the sample is farther than a float32 error bound from all four edges of that bin.  Misses
+//      (~2e-4 of the samples) are appended to a retry list.
 //   2. sphere_hist_resolve_kernel (rare, FP64): re-examines the retry list with the same tests in double
 //      precision and a ~1e-11 margin (rotated stream), or drops NaN / zero vectors (float32 reference stream).
 //      What is still undecided keeps its sample id in the list for the host, which re-bins those few samples
@@ -14,21 +13,24 @@
 #include "common.cuh"
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <mutex>
+#include <utility>
 #include <vector>
 
 namespace {
 
-constexpr int kHistThreads = 384;   // threads per CTA (2 CTAs per SM: 85 registers per thread)
-constexpr int kHistGroup = 16;      // vectors per CTA (4 per thread)
-constexpr int kHistFP = kHistThreads / 4;   // frames covered by one pass of the CTA
+constexpr int kHistThreads = 768;   // default threads per CTA, one CTA per SM (80 registers per thread)
 
 struct HistParams {
   double R[9];        // rotation matrix (row major), identity when no rotation
   double tol_phi;     // angular margin (rad) of the FP64 test
   double tol_cos;     // cos(theta) margin of the FP64 test
   float Rf[9];        // the same matrix in float32 for the fast path
-  float fphi_abs, fphi_rel, fcos;   // fast-path margins (see fast_classify)
+  float pk[6];        // atan polynomial scaled to phi-bin units: atan(t) nbx/(2 pi) ~ t (pk0 + pk1 t^2 + ... + pk5 t^10)
+  float quarter, half;              // nbx/4, nbx/2: a quarter and a half turn in phi-bin units
+  float phi_c0, phi_m1;             // fast phi test: |frac - 1/2| rho1 <= phi_c0 rho1 - phi_m1 (rho1 + |z|)
+  float cos_scale, cos_c0;          // nby/2 ; fast cos test: |frac - 1/2| <= cos_c0
   int nbx, nby;
   int f32_reference;  // 1: no rotation, the reference itself works in float32 -> fast-path misses go to the host
 };
@@ -81,54 +83,80 @@ __device__ __forceinline__ int classify(double x, double y, double z, const Slow
   return 0;
 }
 
-// FP32 fast path margins.  fphi_abs covers the float32 rounding of the rotated coordinates (absolute, rotated
-// path); fphi_rel / fcos the reference's own float32 arctan2/arccos/cos error (unrotated path).
+// Hot kernel (FP32).  For every sample it computes the position of the rotated vector in *bin units* along both
+// histogram axes, u_phi = (atan2(y, x) + pi) nbx / (2 pi) from a degree-11 minimax polynomial of atan on [0,1]
+// (|error| < 2.1e-5 bins at nbx = 72, float32 evaluation included) and u_cos = (z / r + 1) nby / 2, and accepts the
+// bin (floor u_phi, floor u_cos) only if both fractional parts are farther from 0 and 1 than a margin that
+// bounds every float32 effect on them:
+//   phi:  |frac - 1/2| rho1 <= (1/2 - m0) rho1 - m1 (rho1 + |z|),  rho1 = |x| + |y|
+//         (frac - 1/2 is taken as (u - 1/2) - rint(u - 1/2): a tie of the rounding is a sample on an edge, rejected)
+//         m0 = polynomial + evaluation error, m1 (rho1 + |z|) / rho1 >= the angle error caused by the float32
+//         rounding of the rotated x, y (absolute ~3e-7 |v|, so it grows towards the poles);
+//   cos:  |frac - 1/2| <= 1/2 - mc.
+// The unrotated stream has no coordinate rounding (m1 = 0); there m0 / mc hold the reference's own float32
+// arctan2 / arccos / cos error (the caller's tolerances).  NaN, zero, huge and polar vectors need no explicit test:
+// they make one of the comparisons false.  Misses (~2e-4 of the samples) go to the retry list, once per thread and
+// pass rather than per sample, so the common path is branch-free.
 //
-// Hot kernel.  grid.x = vector groups (fastest, so CTAs sharing a frame range run together and the 64-byte
-// DRAM blocks that straddle two groups are fetched once), grid.y = frame blocks.  A CTA owns kHistGroup
-// vectors; thread t works on the four vectors 4*(t&3) .. +3 of frame t>>2 (+128 per pass), i.e. on 48
-// contiguous bytes of the reference's AoS layout -- three LDG.128 when a frame row is a multiple of 16 bytes
-// (nR % 4 == 0), twelve scalar loads otherwise -- and always has the next pass's 48 bytes in flight while it
-// classifies the current ones.  Bins are privatised in shared memory as packed 16-bit counters (an even
-// number of bins per vector; a CTA sees < 65536 frames) and flushed with global atomics at the end.
-template <bool VEC4>
-__global__ void __launch_bounds__(kHistThreads, 2)
-sphere_hist_kernel(const float* __restrict__ vecs, long long nFrames, int nR, int framesPerBlock,
-                   HistParams p, const double2* __restrict__ edge_dir,
-                   unsigned int* __restrict__ counts, long long* __restrict__ amb_idx, int amb_capacity,
-                   int* __restrict__ amb_count) {
+// grid.x = vector groups (fastest, so CTAs sharing a frame range run together and the 64-byte DRAM blocks that
+// straddle two groups are fetched once), grid.y = frame blocks.  A CTA owns `4 << qshift` vectors; thread t works
+// on four consecutive vectors of one frame, i.e. on 48 contiguous bytes of the reference's AoS layout -- three
+// LDG.128 when a frame row is a multiple of 16 bytes (nR % 4 == 0), twelve scalar loads otherwise -- and always has
+// the next pass's 48 bytes in flight while it classifies the current ones.  Bins are privatised in shared memory
+// as 32-bit counters (one CTA per SM owns 16 x 2592 of them at the default 72 x 36) and flushed with global
+// atomics at the end.
+//
+// NBX/NBY > 0 compiles the bin counts (and with them the polynomial, the turn constants and the per-vector
+// histogram offsets) into immediates -- the reference's default 72 x 36; 0 keeps them as kernel parameters.
+constexpr double kAtanK[6] = {0.9999772310256958, -0.33262282609939575, 0.19354039430618286,
+                              -0.1164264902472496, 0.052647337317466736, -0.01171912346035242};
+constexpr double kPiD = 3.141592653589793;
+constexpr int kHistPadLo = 4;   // words before the first histogram: a rejected sample may carry bin -1 (added value 0)
+
+template <int OFF>
+__device__ __forceinline__ void red_shared_add(uint32_t addr, unsigned v) {
+  asm volatile("red.shared.add.u32 [%0+%2], %1;" ::"r"(addr), "r"(v), "n"(OFF) : "memory");
+}
+
+template <bool VEC4, int NBX, int NBY, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
+sphere_hist_kernel(const float* __restrict__ vecs, long long nFrames, int nR, int framesPerBlock, int qshift,
+                   const __grid_constant__ HistParams p, unsigned int* __restrict__ counts,
+                   long long* __restrict__ amb_idx, int amb_capacity, int* __restrict__ amb_count) {
   extern __shared__ __align__(16) unsigned int sh_raw[];
-  float4* const sh_edge = reinterpret_cast<float4*>(sh_raw);
-  unsigned int* const sh_hist = sh_raw + 4 * p.nbx;
-  const int nbx = p.nbx, nby = p.nby;
+  unsigned int* const sh_hist = sh_raw + kHistPadLo;
+  const int nbx = NBX ? NBX : p.nbx, nby = NBY ? NBY : p.nby;
   const int nbins = nbx * nby;
-  const int wordsPerVec = (nbins + 1) >> 1;
   const int tid = threadIdx.x;
-  const int r0 = blockIdx.x * kHistGroup;
-  const int nv = min(kHistGroup, nR - r0);
-  for (int i = tid; i < nv * wordsPerVec; i += kHistThreads) sh_hist[i] = 0u;
-  for (int i = tid; i < nbx; i += kHistThreads) {
-    const double2 lo = edge_dir[i], hi = edge_dir[i + 1];
-    sh_edge[i] = make_float4((float)lo.x, (float)lo.y, (float)hi.x, (float)hi.y);
-  }
+  const int group = 4 << qshift;                            // vectors per CTA
+  const int framesPerPass = THREADS >> qshift;
+  const int r0 = blockIdx.x * group;
+  const int nv = min(group, nR - r0);
+  for (int i = tid; i < nv * nbins; i += THREADS) sh_hist[i] = 0u;
   __syncthreads();
 
   const long long f0 = (long long)blockIdx.y * framesPerBlock;
   const int nfl = (int)min((long long)framesPerBlock, nFrames - f0);
-  const int quad = tid & 3;
+  const int quad = tid & ((1 << qshift) - 1);
   const int nvq = max(0, min(4, nv - 4 * quad));            // valid vectors of this thread
-  int fl = tid >> 2;
-  const uint32_t edge_addr = sr_smem_u32(sh_edge);
-  const uint32_t hist_addr = sr_smem_u32(sh_hist + 4 * quad * wordsPerVec);
-  const uint32_t hist_step = (uint32_t)wordsPerVec * 4u;
+  int fl = tid >> qshift;
+  const uint32_t hist_addr = sr_smem_u32(sh_hist + 4 * quad * nbins);
+  const uint32_t hist_step = (uint32_t)nbins * 4u;
   const float q0 = p.Rf[0], q1 = p.Rf[1], q2 = p.Rf[2], q3 = p.Rf[3], q4 = p.Rf[4], q5 = p.Rf[5], q6 = p.Rf[6],
               q7 = p.Rf[7], q8 = p.Rf[8];
-  const float fphi_abs = p.fphi_abs, fphi_rel = p.fphi_rel, fcos = p.fcos;
-  const float phi_scale = nbx * 0.159154943f, cos_scale = 0.5f * nby, wbin = 2.0f / nby;
-  const size_t passStride = (size_t)kHistFP * nR * 3;
+  constexpr double kScale = NBX / (2.0 * kPiD);
+  const float k0 = NBX ? (float)(kAtanK[0] * kScale) : p.pk[0], k1 = NBX ? (float)(kAtanK[1] * kScale) : p.pk[1],
+              k2 = NBX ? (float)(kAtanK[2] * kScale) : p.pk[2], k3 = NBX ? (float)(kAtanK[3] * kScale) : p.pk[3],
+              k4 = NBX ? (float)(kAtanK[4] * kScale) : p.pk[4], k5 = NBX ? (float)(kAtanK[5] * kScale) : p.pk[5];
+  const float quarter = NBX ? 0.25f * NBX : p.quarter, half = NBX ? 0.5f * NBX : p.half;
+  const float cos_scale = NBY ? 0.5f * NBY : p.cos_scale, fnby = NBY ? (float)NBY : (float)p.nby;
+  const float halfm = half - 0.5f, cos_scalem = cos_scale - 0.5f;      // exact
+  const float phi_c1 = p.phi_c0 - p.phi_m1, phi_m1 = p.phi_m1, cos_c0 = p.cos_c0;
+  const size_t passStride = (size_t)framesPerPass * nR * 3;
   const float* src = vecs + ((size_t)(f0 + fl) * nR + r0 + 4 * quad) * 3;
   long long sidx = (f0 + fl) * nR + r0 + 4 * quad;          // sample id of this thread's first vector
-  const long long sidxStep = (long long)kHistFP * nR;
+  const long long sidxStep = (long long)framesPerPass * nR;
+  const unsigned validMask = (1u << nvq) - 1u;
 
   auto load = [&](float (&d)[12], const float* s) {
     if (VEC4) {
@@ -142,50 +170,59 @@ sphere_hist_kernel(const float* __restrict__ vecs, long long nFrames, int nR, in
     }
   };
   auto process = [&](const float (&d)[12], long long sid) {
+    unsigned miss = 0u;
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const float vx = d[3 * u], vy = d[3 * u + 1], vz = d[3 * u + 2];
       const float x = fmaf(q0, vx, fmaf(q1, vy, q2 * vz));
       const float y = fmaf(q3, vx, fmaf(q4, vy, q5 * vz));
       const float z = fmaf(q6, vx, fmaf(q7, vy, q8 * vz));
-      // NaN, zero, huge or polar vectors need no explicit test: they fail the margin comparisons below
-      // (rsqrtf(0) = inf -> cf = NaN; rho1 = 0 -> |cross| = 0 < mphi) and go to the retry list.
       const float r2 = fmaf(x, x, fmaf(y, y, z * z));
       const float ax = fabsf(x), ay = fabsf(y);
       const float rho1 = ax + ay;
-      // phi candidate from a degree-11 odd minimax polynomial of atan on [0,1] (max error 1.8e-6 rad)
+      // ---- phi, in bin units ----
       const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
       const float t = __fdividef(mn, mx), t2 = t * t;
-      float a = fmaf(t2, -0.01171912346035242f, 0.052647337317466736f);
-      a = fmaf(t2, a, -0.1164264902472496f);
-      a = fmaf(t2, a, 0.19354039430618286f);
-      a = fmaf(t2, a, -0.33262282609939575f);
-      a = fmaf(t2, a, 0.9999772310256958f) * t;
-      if (ay > ax) a = 1.57079632679f - a;
-      if (x < 0.f) a = 3.14159265359f - a;
-      if (y < 0.f) a = -a;
-      int i = (int)floorf(fmaf(a, phi_scale, 3.14159265359f * phi_scale));
-      i = max(0, min(nbx - 1, i));
-      float4 e;   // (cos e_i, sin e_i, cos e_{i+1}, sin e_{i+1})
-      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(e.x), "=f"(e.y), "=f"(e.z), "=f"(e.w) : "r"(edge_addr + i * 16));
-      const float mphi = fmaf(fphi_rel, rho1, fphi_abs * (rho1 + fabsf(z))) + 1e-30f;
-      const float clo = fmaf(e.x, y, -e.y * x);   // rho sin(phi - e_i)
-      const float chi = fmaf(e.z, y, -e.w * x);   // rho sin(phi - e_{i+1})
-      const float cf = z * rsqrtf(r2);
-      int j = (int)floorf(fmaf(cf, cos_scale, cos_scale));
-      j = max(0, min(nby - 1, j));
-      const float elo = fmaf((float)j, wbin, -1.0f), ehi = elo + wbin;
-      const bool ok = (clo >= mphi) && (chi <= -mphi) && (cf - elo >= fcos) && (ehi - cf >= fcos);   // NaN compares false
-      const int bin = i * nby + j;
-      if (u < nvq) {
-        if (ok) {
-          asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(hist_addr + u * hist_step + ((bin >> 1) << 2)),
-                       "r"(1u << ((bin & 1) << 4)) : "memory");
-        } else {   // rare: hand the sample to sphere_hist_resolve_kernel
+      float a = fmaf(t2, k5, k4);
+      a = fmaf(t2, a, k3);
+      a = fmaf(t2, a, k2);
+      a = fmaf(t2, a, k1);
+      a = fmaf(t2, a, k0) * t;                              // [0, nbx/8]
+      if (ay > ax) a = quarter - a;                         // [0, nbx/4]
+      if (x < 0.f) a = half - a;                            // [0, nbx/2]
+      // u - 1/2 along each axis: its nearest integer is the bin, its distance from that integer is |frac - 1/2|
+      const float uphi = copysignf(a, y) + halfm;           // [-1/2, nbx - 1/2]
+      const float fphi = rintf(uphi);
+      const float dphi = fabsf(uphi - fphi);
+      const bool okphi = dphi * rho1 <= fmaf(-phi_m1, fabsf(z), phi_c1 * rho1);
+      // ---- cos(theta), in bin units ----
+      const float ucos = fmaf(z * rsqrtf(r2), cos_scale, cos_scalem);  // [-1/2 - eps, nby - 1/2 + eps]
+      const float fcos = rintf(ucos);
+      const bool okcos = fabsf(ucos - fcos) <= cos_c0;
+      const bool ok = okphi && okcos;                        // NaN compares false
+      // ok implies 0 <= bin < nbins (the fractional parts at and beyond the ends of both ranges fail the margins);
+      // a rejected sample adds 0 to a word inside [-1, nbins + nby] of its vector's histogram (padding both ends).
+      const int bin = (int)fmaf(fphi, fnby, fcos);
+      const uint32_t addr = hist_addr + ((uint32_t)bin << 2);
+      if (NBX && NBY) {
+        const unsigned one = ok ? 1u : 0u;                   // the offset of vector u is an immediate of the instruction
+        if (u == 0) red_shared_add<0>(addr, one);
+        if (u == 1) red_shared_add<4 * NBX * NBY>(addr, one);
+        if (u == 2) red_shared_add<8 * NBX * NBY>(addr, one);
+        if (u == 3) red_shared_add<12 * NBX * NBY>(addr, one);
+      } else {
+        asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr + u * hist_step), "r"(ok ? 1u : 0u) : "memory");
+      }
+      if (!ok) miss |= 1u << u;
+    }
+    miss &= validMask;
+    if (miss) {     // rare: hand the samples to sphere_hist_resolve_kernel
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (miss & (1u << u)) {
           const int slot = atomicAdd(amb_count, 1);
           if (slot < amb_capacity) amb_idx[slot] = sid + u;
         }
-      }
     }
   };
 
@@ -193,24 +230,20 @@ sphere_hist_kernel(const float* __restrict__ vecs, long long nFrames, int nR, in
     float A[12], B[12];
     if (fl < nfl) load(A, src);
     while (fl < nfl) {
-      const bool moreB = fl + kHistFP < nfl;
+      const bool moreB = fl + framesPerPass < nfl;
       if (moreB) load(B, src + passStride);
       process(A, sidx);
       if (!moreB) break;
-      const bool moreA = fl + 2 * kHistFP < nfl;
+      const bool moreA = fl + 2 * framesPerPass < nfl;
       if (moreA) load(A, src + 2 * passStride);
       process(B, sidx + sidxStep);
-      fl += 2 * kHistFP; src += 2 * passStride; sidx += 2 * sidxStep;
+      fl += 2 * framesPerPass; src += 2 * passStride; sidx += 2 * sidxStep;
     }
   }
   __syncthreads();
-  for (int i = tid; i < nv * wordsPerVec; i += kHistThreads) {
+  for (int i = tid; i < nv * nbins; i += THREADS) {
     const unsigned int w = sh_hist[i];
-    if (w == 0u) continue;
-    const int v = i / wordsPerVec, k = i - v * wordsPerVec;
-    const long long g = (long long)(r0 + v) * nbins + 2 * k;
-    if (w & 0xffffu) atomicAdd(&counts[g], w & 0xffffu);
-    if (w >> 16) atomicAdd(&counts[g + 1], w >> 16);
+    if (w) atomicAdd(&counts[(long long)r0 * nbins + i], w);
   }
 }
 
@@ -278,26 +311,52 @@ extern "C" int sr_sphere_hist(const float* d_vecs, long long nFrames, int nR, co
   }
   for (int i = 0; i < 9; ++i) p.Rf[i] = (float)p.R[i];
   p.f32_reference = h_q_rot ? 0 : 1;
-  if (h_q_rot) {   // float32 rounding of the rotated coordinates: ~3e-7 |v| absolute
-    p.fphi_abs = 1.5e-6f; p.fphi_rel = 0.f; p.fcos = 2.0e-6f;
-  } else {         // the caller's tolerances describe the reference's own float32 error
-    p.fphi_abs = 1e-12f; p.fphi_rel = (float)tol_phi; p.fcos = (float)tol_cos;
+  {  // fast-path constants (derivation above sphere_hist_kernel)
+    static const double atan_k[6] = {0.9999772310256958, -0.33262282609939575, 0.19354039430618286,
+                                     -0.1164264902472496, 0.052647337317466736, -0.01171912346035242};
+    const double kPi = 3.141592653589793, scale = nbx / (2.0 * kPi);
+    for (int i = 0; i < 6; ++i) p.pk[i] = (float)(atan_k[i] * scale);
+    p.quarter = 0.25f * nbx; p.half = 0.5f * nbx; p.cos_scale = 0.5f * nby;
+    const double eval_phi = 3.0e-7 * nbx, eval_cos = 1.5e-7 * nby;     // float32 evaluation of u_phi / u_cos, 2x
+    double m0, m1, mc;
+    if (h_q_rot) {   // polynomial 1.7e-6 rad + evaluation 0.7e-6 rad, doubled; coordinate rounding 6e-7 |v| / rho1 rad, doubled
+      m0 = 4.8e-6 * scale + eval_phi; m1 = 1.2e-6 * scale; mc = 2.0e-6 * p.cos_scale + eval_cos;
+    } else {         // the caller's tolerances describe the reference's own float32 error; ours (2.4e-6 rad) on top
+      m0 = (tol_phi + 2.4e-6) * scale + eval_phi; m1 = 0.0; mc = tol_cos * p.cos_scale + eval_cos;
+    }
+    SR_REQUIRE(m0 + m1 < 0.25 && mc < 0.25, "sr_sphere_hist: bins too narrow for the float32 pass (%d x %d)", nbx, nby);
+    p.phi_c0 = (float)(0.5 - m0); p.phi_m1 = (float)m1; p.cos_c0 = (float)(0.5 - mc);
   }
   const int nbins = nbx * nby;
   int dev = 0, max_smem = 0, sms = 0;
   SR_CUDA(cudaGetDevice(&dev));
-  SR_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  SR_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const size_t wordsPerVec = ((size_t)nbins + 1) / 2;
-  const size_t smem = (size_t)kHistGroup * wordsPerVec * 4 + (size_t)nbx * 16;
+  SR_REQUIRE(dev >= 0 && dev < 64, "sr_sphere_hist: device ordinal %d not supported", dev);
+  {  // device limits are looked up once per device: a short histogram call is launch-latency bound
+    static std::mutex attr_mu;
+    static int attr_smem[64] = {0}, attr_sms[64] = {0};
+    std::lock_guard<std::mutex> lock(attr_mu);
+    if (!attr_sms[dev]) {
+      SR_CUDA(cudaDeviceGetAttribute(&attr_smem[dev], cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+      SR_CUDA(cudaDeviceGetAttribute(&attr_sms[dev], cudaDevAttrMultiProcessorCount, dev));
+    }
+    max_smem = attr_smem[dev]; sms = attr_sms[dev];
+  }
+  // vectors per CTA: 16 when their 32-bit bins fit in shared memory (72 x 36: 162 KB), else 8 or 4
+  int qshift = 2;
+  while (qshift > 0 && ((size_t)(4 << qshift) * nbins + kHistPadLo + nby + 4) * 4 > (size_t)max_smem) --qshift;
+  const int group = 4 << qshift;
+  const size_t smem = ((size_t)group * nbins + kHistPadLo + nby + 4) * 4;      // padding: see the kernel's bin comment
   SR_REQUIRE(smem <= (size_t)max_smem, "sr_sphere_hist: %d bins do not fit in shared memory", nbins);
-  const int nGroups = (nR + kHistGroup - 1) / kHistGroup;
-  // one wave of 2 CTAs per SM; a CTA must see fewer than 65536 frames (16-bit privatised counters)
-  long long nFB = std::max(1LL, (2LL * sms) / nGroups);
+  static const int threads_env = [] { const char* e = getenv("SR_HIST_THREADS"); return e ? atoi(e) : 0; }();
+  const int threads = (threads_env == 640 || threads_env == 512 || threads_env == 896 || threads_env == 1024) ? threads_env : kHistThreads;   // tuning hook
+  const int framesPerPass = threads >> qshift;
+  const int nGroups = (nR + group - 1) / group;
+  // one wave of one CTA per SM
+  long long nFB = std::max(1LL, (long long)sms / nGroups);
   long long fpb = (nFrames + nFB - 1) / nFB;
-  fpb = std::min(std::max(fpb, (long long)kHistFP), 32768LL);
+  fpb = std::max(fpb, (long long)framesPerPass);
   nFB = (nFrames + fpb - 1) / fpb;
-  SR_REQUIRE(nFB <= 65535, "sr_sphere_hist: %lld frame blocks exceed the grid limit", nFB);
+  SR_REQUIRE(nFB <= 65535 && fpb <= 2147483647LL, "sr_sphere_hist: %lld frame blocks exceed the grid limit", nFB);
   dim3 grid((unsigned)nGroups, (unsigned)nFB);
   const double2* edge_dir = (const double2*)d_edge_table;
   const double* edge_cos = d_edge_table + 2 * (nbx + 1);
@@ -310,20 +369,36 @@ extern "C" int sr_sphere_hist(const float* d_vecs, long long nFrames, int nR, co
   int* d_amb_start = nullptr;
   {
     std::lock_guard<std::mutex> lock(ring_mu);
-    SR_REQUIRE(dev >= 0 && dev < 64, "sr_sphere_hist: device ordinal %d not supported", dev);
     if (!ring[dev]) SR_CUDA(cudaMalloc(&ring[dev], 256 * sizeof(int)));
     d_amb_start = ring[dev] + (ring_next[dev]++ & 255u);
   }
   sphere_hist_mark_kernel<<<1, 1, 0, st>>>(d_amb_count, amb_capacity, d_amb_start);
-  if (nR % 4 == 0 && ((uintptr_t)d_vecs & 15) == 0) {
-    SR_CUDA(cudaFuncSetAttribute(sphere_hist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    sphere_hist_kernel<true><<<grid, kHistThreads, smem, st>>>(d_vecs, nFrames, nR, (int)fpb, p, edge_dir, d_counts,
-                                                              d_amb_idx, amb_capacity, d_amb_count);
-  } else {
-    SR_CUDA(cudaFuncSetAttribute(sphere_hist_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    sphere_hist_kernel<false><<<grid, kHistThreads, smem, st>>>(d_vecs, nFrames, nR, (int)fpb, p, edge_dir, d_counts,
-                                                               d_amb_idx, amb_capacity, d_amb_count);
+  const bool vec4 = nR % 4 == 0 && ((uintptr_t)d_vecs & 15) == 0;
+  const bool dflt = nbx == 72 && nby == 36;                // the reference's default --histBin
+  void (*kern)(const float*, long long, int, int, int, const HistParams, unsigned int*, long long*, int, int*);
+  if (threads == 1024) kern = vec4 ? (dflt ? sphere_hist_kernel<true, 72, 36, 1024> : sphere_hist_kernel<true, 0, 0, 1024>)
+                                   : (dflt ? sphere_hist_kernel<false, 72, 36, 1024> : sphere_hist_kernel<false, 0, 0, 1024>);
+  else if (threads == 896) kern = vec4 ? (dflt ? sphere_hist_kernel<true, 72, 36, 896> : sphere_hist_kernel<true, 0, 0, 896>)
+                                       : (dflt ? sphere_hist_kernel<false, 72, 36, 896> : sphere_hist_kernel<false, 0, 0, 896>);
+  else if (threads == 640) kern = vec4 ? (dflt ? sphere_hist_kernel<true, 72, 36, 640> : sphere_hist_kernel<true, 0, 0, 640>)
+                                  : (dflt ? sphere_hist_kernel<false, 72, 36, 640> : sphere_hist_kernel<false, 0, 0, 640>);
+  else if (threads == 512) kern = vec4 ? (dflt ? sphere_hist_kernel<true, 72, 36, 512> : sphere_hist_kernel<true, 0, 0, 512>)
+                                       : (dflt ? sphere_hist_kernel<false, 72, 36, 512> : sphere_hist_kernel<false, 0, 0, 512>);
+  else kern = vec4 ? (dflt ? sphere_hist_kernel<true, 72, 36, 768> : sphere_hist_kernel<true, 0, 0, 768>)
+                   : (dflt ? sphere_hist_kernel<false, 72, 36, 768> : sphere_hist_kernel<false, 0, 0, 768>);
+  {  // opt in to the large dynamic shared memory; the limit of a (kernel, device) is only ever raised
+    static std::mutex fa_mu;
+    static std::vector<std::pair<std::pair<const void*, int>, size_t>> limit;
+    std::lock_guard<std::mutex> lock(fa_mu);
+    const std::pair<const void*, int> key((const void*)kern, dev);
+    auto it = std::find_if(limit.begin(), limit.end(), [&](const auto& e) { return e.first == key; });
+    if (it == limit.end() || it->second < smem) {
+      SR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      if (it == limit.end()) limit.push_back({key, smem}); else it->second = smem;
+    }
   }
+  kern<<<grid, threads, smem, st>>>(d_vecs, nFrames, nR, (int)fpb, qshift, p, d_counts, d_amb_idx, amb_capacity,
+                                    d_amb_count);
   SR_CUDA(cudaGetLastError());
   sphere_hist_resolve_kernel<<<sms, 256, 0, st>>>(d_vecs, nR, p, edge_dir, edge_cos, d_counts, d_amb_idx, amb_capacity,
                                                   d_amb_count, d_amb_start);

@@ -44,6 +44,19 @@ def test_hist_vs_oracle_same_host(nR, frames, rot):
     assert h.sum() == frames * nR
 
 
+@pytest.mark.parametrize("nbx", [10, 120, 144])
+def test_hist_other_bin_counts(nbx):
+    """Non-default --histBin: runtime bin constants, and 8 / 4 vectors per CTA when 16 histograms do not fit."""
+    from spinrelax_b200 import hist, synth
+    v = synth.nh_vectors(3000, 21, seed=nbx)
+    for q in (np.array([0.2, 0.5, -0.7, 0.1]), None):
+        with np.errstate(all="ignore"):
+            h, e = hist.sphere_histogram(v, q, nbx)
+            ho, eo = ct_oracle.sphere_histogram(v, q, nbins_phi=nbx)
+        assert np.array_equal(h.astype(np.int64), ho.astype(np.int64)) and h.sum() == 3000 * 21
+        assert np.array_equal(e[0], eo[0]) and np.array_equal(e[1], eo[1])
+
+
 def test_hist_uniform_sphere_and_ties():
     """Uniform vectors touch every bin; axis-aligned and grid-aligned vectors sit exactly on edges."""
     rng = np.random.default_rng(5)
