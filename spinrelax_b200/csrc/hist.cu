@@ -351,8 +351,21 @@ extern "C" int sr_sphere_hist(const float* d_vecs, long long nFrames, int nR, co
   const int threads = (threads_env == 640 || threads_env == 512 || threads_env == 896 || threads_env == 1024) ? threads_env : kHistThreads;   // tuning hook
   const int framesPerPass = threads >> qshift;
   const int nGroups = (nR + group - 1) / group;
-  // one wave of one CTA per SM
-  long long nFB = std::max(1LL, (long long)sms / nGroups);
+  // One CTA per SM at a time.  The number of frame blocks minimises waves x (samples per CTA + fixed cost per CTA):
+  // the grid comes out close to a whole number of waves, and unequal CTAs (a last group with fewer vectors)
+  // backfill when there are several waves.  The fixed cost -- zeroing and flushing the CTA's counters, ~3 us --
+  // is worth ~10^4 samples; a CTA always sees at least 16 passes.
+  long long nFB = 1;
+  {
+    const long long maxFB = std::max(1LL, std::min(65535LL, nFrames / (16LL * framesPerPass)));
+    const long long hi = std::min(maxFB, (32LL * sms) / nGroups + 1);
+    double best = 1e300;
+    for (long long cand = 1; cand <= hi; ++cand) {
+      const long long total = cand * nGroups, waves = (total + sms - 1) / sms;
+      const double cost = (double)waves * ((double)group * (double)((nFrames + cand - 1) / cand) + 1.0e4);
+      if (cost < best * (1.0 - 1e-9)) { best = cost; nFB = cand; }
+    }
+  }
   long long fpb = (nFrames + nFB - 1) / nFB;
   fpb = std::max(fpb, (long long)framesPerPass);
   nFB = (nFrames + fpb - 1) / fpb;
