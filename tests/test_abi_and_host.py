@@ -69,3 +69,27 @@ def test_product_never_imports_oracle():
                 with open(os.path.join(dirpath, f)) as fp:
                     src = fp.read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+
+
+def test_spherical_host_side_matches_reference(golden, tmp_path):
+    """gm.rtp_to_xyz (host) against the real function; print_s3d against what the shipped writer produces before it
+    stops (its first set), continued in the same format; xyz_to_rtp refuses to run without a GPU."""
+    from spinrelax_b200 import gm, io_formats
+    g = golden("rtp.npz")
+    assert np.array_equal(gm.rtp_to_xyz(g["pt"], vaxis=-1, bUnit=True), g["back"])
+    assert np.array_equal(gm.rtp_to_xyz(np.array([1.3, 0.4, 2.1])), g["back1"])
+    ax0 = gm.rtp_to_xyz(np.ascontiguousarray(np.moveaxis(g["pt"], -1, 0)), vaxis=0, bUnit=True)
+    assert np.array_equal(np.moveaxis(ax0, 0, -1), g["back"])
+    rtp = np.transpose(g["rtp64"], (1, 0, 2))
+    fn = tmp_path / "pt.dat"
+    io_formats.print_s3d(str(fn), ["A", "B", "C", "D", "E"], rtp, (1, 2))
+    txt = fn.read_text()
+    head = str(g["s3d_partial"])
+    assert bool(g["s3d_crashed"]) and txt.startswith(head)
+    lines = txt.splitlines()
+    assert len(lines) == 5 * 702 and lines[702] == '@s1 legend "B"' and lines[-1] == "&"
+    assert lines[703] == "%g %g" % (rtp[1, 0, 1], rtp[1, 0, 2])
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            gm.xyz_to_rtp(g["vecs"])
