@@ -28,10 +28,10 @@ __device__ void evaluate(const double* __restrict__ t, const double* __restrict_
                          int L, const double* q, FitShared& sh, double* outJtJ, double* outJtr, double* outCost) {
   constexpr int nc = nP / 2;
   constexpr bool free_s2 = (nP & 1);
-  double C[4], tau[4];
+  double C[4], itau[4];
   double sumC = 0.0;
 #pragma unroll
-  for (int i = 0; i < nc; ++i) { C[i] = q[i]; tau[i] = q[nc + i]; sumC += C[i]; }
+  for (int i = 0; i < nc; ++i) { C[i] = q[i]; itau[i] = 1.0 / q[nc + i]; sumC += C[i]; }   // one division per tau, not per point
   const double S2 = free_s2 ? q[nP - 1] : 1.0 - sumC;
   constexpr int nUsed = nP * (nP + 1) / 2 + nP + 1;
   double acc[nUsed];
@@ -44,10 +44,10 @@ __device__ void evaluate(const double* __restrict__ t, const double* __restrict_
     double f = S2;
 #pragma unroll
     for (int i = 0; i < nc; ++i) {
-      const double e = exp(-tk / tau[i]);
+      const double e = exp(-tk * itau[i]);
       f += C[i] * e;
       g[i] = (e - (free_s2 ? 0.0 : 1.0)) * w;
-      g[nc + i] = C[i] * e * tk / (tau[i] * tau[i]) * w;
+      g[nc + i] = C[i] * e * tk * (itau[i] * itau[i]) * w;
     }
     if (free_s2) g[nP - 1] = w;
     const double r = (f - y[k]) * w;
@@ -67,23 +67,24 @@ __device__ void evaluate(const double* __restrict__ t, const double* __restrict_
     if (lane == 0) sh.red[warp][i] = v;
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    int m = 0;
-    for (int a = 0; a < nP; ++a)
-      for (int b = a; b < nP; ++b) {
-        double s = 0.0;
-        for (int w2 = 0; w2 < kFitThreads / 32; ++w2) s += sh.red[w2][m];
-        outJtJ[a * nP + b] = s; outJtJ[b * nP + a] = s;
-        ++m;
-      }
-    for (int a = 0; a < nP; ++a) {
-      double s = 0.0;
-      for (int w2 = 0; w2 < kFitThreads / 32; ++w2) s += sh.red[w2][m];
-      outJtr[a] = s; ++m;
+  // one thread per reduced quantity combines the warps' partial sums (the solver iterates one residue per CTA, so
+  // the time of a fit is the latency of this chain, not its throughput)
+  if (threadIdx.x < nUsed) {
+    const int m = threadIdx.x;
+    double s2 = 0.0;
+#pragma unroll
+    for (int w2 = 0; w2 < kFitThreads / 32; ++w2) s2 += sh.red[w2][m];
+    constexpr int nTri = nP * (nP + 1) / 2;
+    if (m < nTri) {
+      int a = 0, rem = m;                      // m -> (a, b >= a) of the packed upper triangle
+      while (rem >= nP - a) { rem -= nP - a; ++a; }
+      const int b = a + rem;
+      outJtJ[a * nP + b] = s2; outJtJ[b * nP + a] = s2;
+    } else if (m < nTri + nP) {
+      outJtr[m - nTri] = s2;
+    } else {
+      *outCost = s2;
     }
-    double s = 0.0;
-    for (int w2 = 0; w2 < kFitThreads / 32; ++w2) s += sh.red[w2][m];
-    *outCost = s;
   }
   __syncthreads();
 }
@@ -100,27 +101,29 @@ __device__ bool lm_step(const double* A, const double* g, const bool* fixed, int
     M[i * m + i] += lam * (dii > 0.0 ? dii : 1.0);
     b[i] = -g[idx[i]];
   }
+  double inv[kMaxP];                           // 1 / L_jj: one rsqrt per column instead of a division per element
   for (int j = 0; j < m; ++j) {
     double s = M[j * m + j];
     for (int k = 0; k < j; ++k) s -= M[j * m + k] * M[j * m + k];
-    if (!(s > 0.0)) return false;
-    const double ljj = sqrt(s);
-    M[j * m + j] = ljj;
+    if (!(s > 0.0) || !(s < 1e300)) return false;
+    const double rj = rsqrt(s);
+    inv[j] = rj;
+    M[j * m + j] = s * rj;
     for (int i = j + 1; i < m; ++i) {
       double v = M[i * m + j];
       for (int k = 0; k < j; ++k) v -= M[i * m + k] * M[j * m + k];
-      M[i * m + j] = v / ljj;
+      M[i * m + j] = v * rj;
     }
   }
   for (int i = 0; i < m; ++i) {
     double v = b[i];
     for (int k = 0; k < i; ++k) v -= M[i * m + k] * b[k];
-    b[i] = v / M[i * m + i];
+    b[i] = v * inv[i];
   }
   for (int i = m - 1; i >= 0; --i) {
     double v = b[i];
     for (int k = i + 1; k < m; ++k) v -= M[k * m + i] * b[k];
-    b[i] = v / M[i * m + i];
+    b[i] = v * inv[i];
   }
   for (int i = 0; i < m; ++i) d[idx[i]] = b[i];
   return true;
@@ -164,17 +167,16 @@ ct_fit_lm_kernel(const double* __restrict__ T, const double* __restrict__ Y, con
       // per-coordinate fraction-to-boundary rule: a coordinate whose step would leave the box moves 99.5% of the
       // way to that bound instead (the trial point stays strictly inside, as SciPy's TRF iterates do, so a wild
       // step can never park tau on 0 where the model has no gradient); the other coordinates keep their step.
-      double smax = 0.0;
-      int truncated = 0;
+      int tiny = 1, truncated = 0;          // tiny: every |step_i| < 1e-15 |p_i|
       for (int i = 0; i < nP; ++i) {
         double q = sh.p[i] + d[i];
         if (q < sh.lo[i]) { q = sh.p[i] - 0.995 * (sh.p[i] - sh.lo[i]); truncated = 1; }
         else if (q > sh.hi[i]) { q = sh.p[i] + 0.995 * (sh.hi[i] - sh.p[i]); truncated = 1; }
-        smax = fmax(smax, fabs(q - sh.p[i]) / (fabs(sh.p[i]) + 1e-300));
+        if (!(fabs(q - sh.p[i]) < 1e-15 * (fabs(sh.p[i]) + 1e-300))) tiny = 0;
         sh.ptry[i] = q;
       }
       sh.trunc = truncated;
-      sh.flag = ok ? (smax < 1e-15 ? 2 : 1) : 0;
+      sh.flag = ok ? (tiny ? 2 : 1) : 0;
     }
     __syncthreads();
     const int flag = sh.flag, trunc = sh.trunc;
