@@ -99,9 +99,11 @@ void sr_release_host_cache(void);
  * d_vecs: (nFrames, nR, 3) float32 AoS (the reference layout after the reshape at :535-536).
  * h_q_rot: host pointer to (w,x,y,z) or NULL for no rotation (float32 path of the reference).
  * d_edge_table: 2*(nbx+1) doubles (cos e_i, sin e_i of the phi edges) followed by the nby+1 cos(theta)
- * edges, as np.histogramdd builds them.  Counts are ADDED into d_counts [nR][nbx][nby] (uint32).
- * Two launches: the FP32 hot pass counts every sample it can place with a float32 margin and appends the flat
- * sample index (frame*nR + r) of the others (~1e-4 of the stream) to d_amb_idx (up to amb_capacity;
+ * edges, as np.histogramdd builds them (np.linspace over (-pi,pi) and (-1,1): the hot pass assumes uniform bins;
+ * the table serves the FP64 pass).  Counts are ADDED into d_counts [nR][nbx][nby] (uint32).
+ * Two passes (three launches with the marker of the retry list): the FP32 hot pass counts every sample it can
+ * place with a float32 error margin and appends the flat sample index (frame*nR + r) of the others (~3e-4 of the
+ * stream) to d_amb_idx (up to amb_capacity;
  * *d_amb_count keeps counting beyond it, so amb_capacity bounds the retry list, not only the final list); the
  * FP64 resolve pass then re-examines that list, counts what is farther than tol_phi (rad) / tol_cos from every
  * bin edge and overwrites those entries with -1.  Entries that are still >= 0 afterwards are samples the caller
