@@ -32,15 +32,12 @@ def curvefit_exponential(DeltaT, *params):
 KERNEL_EVENTS = None      # set to a list to collect (start, end) CUDA event pairs around every sr_ct_fit_lm launch
 
 
-def gpu_curve_fit(t, y, sigma, p0, lo, hi):
-    """Batched bounded least squares.  t, y, sigma: (nR, L) (sigma may be None); p0, lo, hi: (nR, nP).
-    Returns popt (nR,nP), pcov (nR,nP,nP) formed like scipy.optimize.curve_fit (pinv of J^T J scaled by
-    2 cost/(M-n)), cost (nR,), status (nR,2)."""
+def _device_solve(t, y, sigma, p0, lo, hi):
+    """sr_ct_fit_lm on (nR, L) curves: returns popt (nR,nP), J^T J at the optimum (nR,nP,nP), cost (nR,), status (nR,2)."""
     torch = _lib.require_cuda()
     lib = _lib.load()
     dev = torch.device("cuda")
     f = lambda a: torch.from_numpy(np.array(a, dtype=np.float64, order='C')).to(dev)   # noqa: E731
-    t, y, p0 = np.atleast_2d(t), np.atleast_2d(y), np.atleast_2d(p0)
     nR, L = y.shape
     nP = p0.shape[1]
     td, yd, p0d, lod, hid = f(np.broadcast_to(t, (nR, L))), f(y), f(p0), f(np.broadcast_to(lo, (nR, nP))), \
@@ -60,9 +57,13 @@ def gpu_curve_fit(t, y, sigma, p0, lo, hi):
     if KERNEL_EVENTS is not None:
         ev[1].record()
         KERNEL_EVENTS.append(ev)
-    popt, JtJ, cost, status = popt.cpu().numpy(), JtJ.cpu().numpy(), cost.cpu().numpy(), status.cpu().numpy()
-    # scipy.optimize.curve_fit: SVD of J, drop singular values <= eps*max(M,n)*s0, pcov = V S^-2 V^T * 2 cost/(M-n);
-    # here from the eigen-decomposition of J^T J, batched over the residues
+    return popt.cpu().numpy(), JtJ.cpu().numpy(), cost.cpu().numpy(), status.cpu().numpy()
+
+
+def pcov_from_normal_matrix(JtJ, cost, L):
+    """Covariance the way scipy.optimize.curve_fit forms it (SVD of J, singular values <= eps*max(M,n)*s0 dropped,
+    pcov = V S^-2 V^T * 2 cost/(M-n)), from the eigen-decomposition of J^T J, batched over the residues."""
+    nP = JtJ.shape[-1]
     bad = ~np.all(np.isfinite(JtJ), axis=(1, 2))       # diverged fits: keep LAPACK away from NaNs, mark them below
     if np.any(bad):
         JtJ = JtJ.copy()
@@ -78,7 +79,15 @@ def gpu_curve_fit(t, y, sigma, p0, lo, hi):
     else:
         pcov[:] = np.inf
     pcov[bad] = np.nan
-    return popt, pcov, cost, status
+    return pcov
+
+
+def gpu_curve_fit(t, y, sigma, p0, lo, hi):
+    """Batched bounded least squares.  t, y, sigma: (nR, L) (sigma may be None); p0, lo, hi: (nR, nP).
+    Returns popt (nR,nP), pcov (nR,nP,nP) formed like scipy.optimize.curve_fit, cost (nR,), status (nR,2)."""
+    t, y, p0 = np.atleast_2d(t), np.atleast_2d(y), np.atleast_2d(p0)
+    popt, JtJ, cost, status = _device_solve(t, y, sigma, p0, lo, hi)
+    return popt, pcov_from_normal_matrix(JtJ, cost, y.shape[1]), cost, status
 
 
 # ---- containers ------------------------------------------------------------------------------------

@@ -141,3 +141,42 @@ def test_fit_selection_ladder_host_logic(golden, monkeypatch):
             assert rel_err(np.asarray(m.C), row[3:3 + nc]) < 1e-7 and rel_err(np.asarray(m.tau), row[7:7 + nc]) < 1e-7
         a, b = out["vector"].model[k], out["loop"].model[k]
         assert np.array_equal(a.C, b.C) and np.array_equal(a.tau, b.tau) and a.S2 == b.S2
+
+
+def test_pcov_from_normal_matrix_matches_scipy(golden):
+    """curve_fit's covariance rebuilt from J^T J and the cost at SciPy's own optimum (the host half of gpu_curve_fit)."""
+    from scipy.optimize import curve_fit
+    from oracle import fit_oracle
+    from spinrelax_b200 import fitct
+    g = golden("fit.npz")
+    t, Ct, dCt = g["t"], g["Ct"], g["dCt"]
+    for nP in (2, 3, 5):
+        nc = nP // 2
+        JtJ, cost, ref, popts = [], [], [], []
+        for i in range(len(Ct)):
+            p0 = fit_oracle.initial_guess(t, Ct[i], nP)[0]
+            popt, pcov = curve_fit(fit_oracle.model_curve, t, Ct[i], sigma=dCt[i], p0=p0, bounds=fit_oracle.bounds(nP, t[-1] * 10))
+            C, tau = popt[:nc], popt[nc:2 * nc]
+            e = np.exp(-t[None] / tau[:, None])
+            J = np.zeros((len(t), nP))
+            J[:, :nc] = (e - (0.0 if nP % 2 else 1.0)).T
+            J[:, nc:2 * nc] = (C[:, None] * e * t[None] / tau[:, None] ** 2).T
+            if nP % 2:
+                J[:, -1] = 1.0
+            J /= dCt[i][:, None]
+            r = (fit_oracle.model_curve(t, *popt) - Ct[i]) / dCt[i]
+            JtJ.append(J.T @ J); cost.append(0.5 * r @ r); ref.append(pcov)
+            popts.append(popt)
+        ours = fitct.pcov_from_normal_matrix(np.array(JtJ), np.array(cost), len(t))
+        n_well = 0
+        for a, b, popt in zip(ours, ref, popts):
+            if not np.all(np.isfinite(b)):
+                continue
+            da, db = np.sqrt(np.diag(a)), np.sqrt(np.diag(b))
+            # the over-fitting flag of the ladder (any error larger than its parameter) must come out the same; SciPy
+            # differentiates numerically, so only fits that are not flagged have a covariance comparable digit by digit
+            assert np.any(da > popt) == np.any(db > popt)
+            if not np.any(db > popt):
+                assert np.allclose(da, db, rtol=2e-3)
+                n_well += 1
+        assert n_well >= 3 or nP == 5
