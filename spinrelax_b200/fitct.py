@@ -444,9 +444,26 @@ class autoCorrelations:
                 q_sum = ~((S2_state + sumC0) > 1.0)
                 C, tau = popt[:, :nc], popt[:, nc:2 * nc]
                 S2 = popt[:, -1] if fast else 1.0 - np.sum(C, axis=1)
-                model = zeta[a][:, None] * (S2[:, None] + np.sum(C[:, :, None] * np.exp(-1.0 * T[a][:, None, :] / tau[:, :, None]),
-                                                                  axis=1))
-                chi = np.mean(np.square(model - Y[a]), axis=1) if SG is None else np.mean(np.square(model - Y[a]) / SG[a], axis=1)
+                # model = zeta (S2 + sum_c C_c exp(-t / tau_c)), one component at a time in two (n, L) arrays: the
+                # same operations in the same order as the (n, nc, L) broadcast, without its temporaries
+                Ta = T if a.size == n else T[a]
+                ntau = -tau                                   # t / (-tau) == (-1.0 * t) / tau exactly
+                model = np.empty_like(Ta)
+                buf = np.empty_like(Ta) if nc > 1 else None
+                for c in range(nc):
+                    dst = model if c == 0 else buf
+                    np.divide(Ta, ntau[:, c:c + 1], out=dst)
+                    np.exp(dst, out=dst)
+                    np.multiply(C[:, c:c + 1], dst, out=dst)
+                    if c:
+                        model += buf
+                model += S2[:, None]
+                model *= zeta[a][:, None]
+                model -= Y if a.size == n else Y[a]
+                np.square(model, out=model)
+                if SG is not None:
+                    model /= SG if a.size == n else SG[a]
+                chi = np.mean(model, axis=1)
             chi = np.where(finite, chi, np.inf)
             q_over, q_sum = np.where(finite, q_over, True), np.where(finite, q_sum, True)
             ok = finite & q_over & q_sum
