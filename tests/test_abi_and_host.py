@@ -141,6 +141,7 @@ def test_fit_selection_ladder_host_logic(golden, monkeypatch):
             assert rel_err(np.asarray(m.C), row[3:3 + nc]) < 1e-7 and rel_err(np.asarray(m.tau), row[7:7 + nc]) < 1e-7
         a, b = out["vector"].model[k], out["loop"].model[k]
         assert np.array_equal(a.C, b.C) and np.array_equal(a.tau, b.tau) and a.S2 == b.S2
+        assert a.chiSq == b.chiSq and rel_err(a.chiSq, row[1]) < 1e-8
 
 
 def test_pcov_from_normal_matrix_matches_scipy(golden):
