@@ -181,6 +181,39 @@ def golden_rtp():
          back1=back1)
 
 
+def golden_qs():
+    """The REAL host-side quaternion helpers of transforms3d_supplement.py (with the transforms3d stand-in of
+    oracle/_stubs) that SURVEY 8b lists as importable surface."""
+    qs = ref_loader.module("transforms3d_supplement")
+    rng = np.random.default_rng(synth.BASE_SEED + 41)
+    q1 = rng.standard_normal((50, 4)); q1 /= np.linalg.norm(q1, axis=1, keepdims=True)
+    q2 = rng.standard_normal((50, 4)); q2 /= np.linalg.norm(q2, axis=1, keepdims=True)
+    q32 = q1.astype(np.float32)
+    v = rng.standard_normal((50, 3))
+    v[7] = 0.0                                                     # 0/0 -> 0 in vecnorm_NDarray
+    frames = []
+    for k in range(12):                                            # right-handed orthonormal frames (eigenvector-like)
+        A = np.linalg.qr(rng.standard_normal((3, 3)))[0]
+        if np.linalg.det(A) < 0:
+            A[:, 2] *= -1
+        frames.append(A.T)                                         # rows are the axes
+    frames = np.array(frames)
+    with np.errstate(all="ignore"):
+        out = dict(
+            q1=q1, q2=q2, v=v, frames=frames,
+            mult=qs.quat_mult_simd(q1, q2), mult_mixed=qs.quat_mult_simd(qs.quat_invert(q32[:-1]), q32[1:]),
+            invert=qs.quat_invert(q1), invert32=qs.quat_invert(q32),
+            reduce=qs.quat_reduce_simd(q1), reduce_ref=qs.quat_reduce_simd(q1, qref=q2[0]),
+            reduce_ax0=qs.quat_reduce_simd(np.ascontiguousarray(q1.T), axis=0),
+            vecnorm=qs.vecnorm_NDarray(v), vecnorm1=qs.vecnorm_NDarray(v[3]), vecnorm_ax0=qs.vecnorm_NDarray(v.T.copy(), axis=0),
+            v1v2=np.array([qs.quat_v1v2(qs.vecnorm_NDarray(v[i]), qs.vecnorm_NDarray(v[i + 1])) for i in range(8, 20)]),
+            frame_min=np.array([qs.quat_frame_transform_min(f) for f in frames]),
+            rot_small=qs.rotate_vector_simd(v[:9], q1[0]), rot_perq=qs.rotate_vector_simd(v, q1),
+            rot_unnorm=qs.rotate_vector_simd(v[:9], 2.5 * q1[1]),
+        )
+    save("qs.npz", **out)
+
+
 def golden_dq(refdq):
     q = synth.quaternion_walk(6000, seed=synth.BASE_SEED + 31, sigma=(0.01, 0.015, 0.03))     # float32 (G2)
     lags = [5, 10, 40, 100, 333, 1000, 2999]
@@ -473,6 +506,7 @@ def main():
     golden_traj(refct)
     golden_hist(refct)
     golden_rtp()
+    golden_qs()
     golden_dq(refdq)
     golden_dq_multi(refdq)
     golden_fit()

@@ -181,3 +181,33 @@ def test_pcov_from_normal_matrix_matches_scipy(golden):
                 assert np.allclose(da, db, rtol=2e-3)
                 n_well += 1
         assert n_well >= 3 or nP == 5
+
+
+def test_quaternion_helpers_match_reference(golden):
+    """Host-side mirrors of transforms3d_supplement.py (SURVEY 8b importable surface) against the real module."""
+    from spinrelax_b200 import qs
+    g = golden("qs.npz")
+    q1, q2, v, q32 = g["q1"], g["q2"], g["v"], g["q1"].astype(np.float32)
+    assert np.allclose(qs.quat_mult_simd(q1, q2), g["mult"], rtol=0, atol=1e-15)
+    mixed = qs.quat_mult_simd(qs.quat_invert(q32[:-1]), q32[1:])
+    assert mixed.dtype == g["mult_mixed"].dtype and np.allclose(mixed, g["mult_mixed"], rtol=0, atol=1e-15)
+    assert np.array_equal(qs.quat_invert(q1), g["invert"])
+    inv32 = qs.quat_invert(q32)
+    assert inv32.dtype == np.float64 and np.array_equal(inv32, g["invert32"])
+    assert np.array_equal(qs.quat_reduce_simd(q1), g["reduce"])
+    assert np.array_equal(qs.quat_reduce_simd(q1, qref=q2[0]), g["reduce_ref"])
+    assert np.array_equal(qs.quat_reduce_simd(np.ascontiguousarray(q1.T), axis=0), g["reduce_ax0"])
+    with np.errstate(all="ignore"):
+        assert np.array_equal(qs.vecnorm_NDarray(v), g["vecnorm"]) and np.array_equal(qs.vecnorm_NDarray(v[3]), g["vecnorm1"])
+        assert np.array_equal(qs.vecnorm_NDarray(v.T.copy(), axis=0), g["vecnorm_ax0"])
+        u = qs.vecnorm_NDarray(v)
+    got = np.array([qs.quat_v1v2(u[i], u[i + 1]) for i in range(8, 20)])
+    assert np.allclose(got, g["v1v2"], rtol=0, atol=1e-14)
+    fm = np.array([qs.quat_frame_transform_min(f) for f in g["frames"]])
+    assert np.allclose(fm, g["frame_min"], rtol=0, atol=1e-13)
+    # small inputs / per-vector quaternions stay on the host formula (no GPU needed)
+    assert np.allclose(qs.rotate_vector_simd(v[:9], q1[0]), g["rot_small"], rtol=0, atol=1e-15)
+    assert np.allclose(qs.rotate_vector_simd(v, q1), g["rot_perq"], rtol=0, atol=1e-15)
+    assert np.allclose(qs.rotate_vector_simd(v[:9], 2.5 * q1[1]), g["rot_unnorm"], rtol=0, atol=1e-15)
+    R = qs.rotation_matrix(q1[0])
+    assert np.allclose(v[:9] @ R.T, g["rot_small"], rtol=0, atol=1e-14)
