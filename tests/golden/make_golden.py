@@ -214,6 +214,44 @@ def golden_qs():
     save("qs.npz", **out)
 
 
+def golden_io():
+    """Text produced / parsed by the REAL general_scripts.py, plumedcolvario.py and dxio.py writers and readers."""
+    import tempfile
+    gs = ref_loader.module("general_scripts")
+    pl = ref_loader.module("plumedcolvario")
+    dx = ref_loader.module("dxio")
+    rng = np.random.default_rng(synth.BASE_SEED + 51)
+    x = (np.arange(7) + 1) * 10.0
+    y1 = rng.standard_normal(7)
+    y2 = rng.standard_normal((3, 7))
+    ct = np.stack((rng.random((4, 7)).astype(np.float32), (rng.random((4, 7)) * 1e-3).astype(np.float32)), axis=-1)   # (nR, L, 2) float32
+    hist = rng.integers(0, 50, (6, 4)).astype(np.float64)
+    edges = [np.linspace(-np.pi, np.pi, 7), np.linspace(-1, 1, 5)]
+    vol = rng.random((3, 4, 5))
+    q = synth.quaternion_walk(12, seed=synth.BASE_SEED + 52)
+    out = {}
+    with tempfile.TemporaryDirectory() as td, quiet():
+        f = td + "/f"
+        gs.print_xylist(f, x, y1); out["xylist_1d"] = open(f).read()
+        gs.print_xylist(f, x, y2); out["xylist_2d"] = open(f).read()
+        gs.print_xylist(f, x, y2, True, header="# head"); out["xylist_cols"] = open(f).read()
+        gs.print_sxylist(f, ["1", "2", "7", "9"], x, ct, header=["# a", "# b"]); out["sxylist"] = open(f).read()
+        legs, lx, ly, ldy = gs.load_sxydylist(f, "legend")
+        out["sxy_legs"], out["sxy_x"], out["sxy_y"], out["sxy_dy"] = np.array(legs), np.array(lx), np.array(ly), np.array(ldy)
+        gs.print_gplot_hist(f, hist, edges, header="# h", bSphere=True); out["gplot_sphere"] = open(f).read()
+        gs.print_gplot_hist(f, hist, edges, header="# h", bSphere=False); out["gplot_flat"] = open(f).read()
+        dx.write_to_dx(f, vol, (3, 4, 5), [-1.0, -0.5, 0.25], np.diag([0.5, 0.25, 0.125]), "nm"); out["dx"] = open(f).read()
+        with open(f, "w") as fp:
+            fp.write("#! FIELDS time q.w q.x q.y q.z\n#! SET something 1\n")
+            for i, r in enumerate(q):
+                fp.write(" %f %16g %16g %16g %16g\n" % (i * 0.1234567, *[float(v) for v in r]))
+        out["plumed_text"] = open(f).read()
+        names, data = pl.read_from_plumedprint(f)
+        out["plumed_names"], out["plumed_data"] = np.array(names), np.array(data)
+    save("io.npz", x=x, y1=y1, y2=y2, ct=ct, hist=hist, edges_phi=edges[0], edges_cos=edges[1], vol=vol,
+         **{k: np.array(v) for k, v in out.items()})
+
+
 def golden_dq(refdq):
     q = synth.quaternion_walk(6000, seed=synth.BASE_SEED + 31, sigma=(0.01, 0.015, 0.03))     # float32 (G2)
     lags = [5, 10, 40, 100, 333, 1000, 2999]
@@ -507,6 +545,7 @@ def main():
     golden_hist(refct)
     golden_rtp()
     golden_qs()
+    golden_io()
     golden_dq(refdq)
     golden_dq_multi(refdq)
     golden_fit()

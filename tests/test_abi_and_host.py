@@ -211,3 +211,33 @@ def test_quaternion_helpers_match_reference(golden):
     assert np.allclose(qs.rotate_vector_simd(v[:9], 2.5 * q1[1]), g["rot_unnorm"], rtol=0, atol=1e-15)
     R = qs.rotation_matrix(q1[0])
     assert np.allclose(v[:9] @ R.T, g["rot_small"], rtol=0, atol=1e-14)
+
+
+def test_text_writers_and_readers_match_reference(golden, tmp_path):
+    """io_formats against text written / parsed by the real general_scripts.py, plumedcolvario.py and dxio.py."""
+    from spinrelax_b200 import io_formats as io
+    g = golden("io.npz")
+    f = str(tmp_path / "f")
+    x, y1, y2, ct = g["x"], g["y1"], g["y2"], g["ct"]
+    edges = [g["edges_phi"], g["edges_cos"]]
+
+    def wrote(fn, *a, **k):
+        fn(f, *a, **k)
+        return open(f).read()
+
+    assert wrote(io.print_xylist, x, y1) == str(g["xylist_1d"])
+    assert wrote(io.print_xylist, x, y2) == str(g["xylist_2d"])
+    assert wrote(io.print_xylist, x, y2, True, header="# head") == str(g["xylist_cols"])
+    assert wrote(io.print_sxylist, ["1", "2", "7", "9"], x, ct, header=["# a", "# b"]) == str(g["sxylist"])
+    legs, lx, ly, ldy = io.load_sxydylist(f, "legend")
+    assert list(legs) == list(g["sxy_legs"])
+    assert np.array_equal(np.array(lx), g["sxy_x"]) and np.array_equal(np.array(ly), g["sxy_y"])
+    assert np.array_equal(np.array(ldy), g["sxy_dy"])
+    assert wrote(io.print_gplot_hist, g["hist"], edges, header="# h", bSphere=True) == str(g["gplot_sphere"])
+    assert wrote(io.print_gplot_hist, g["hist"], edges, header="# h", bSphere=False) == str(g["gplot_flat"])
+    assert wrote(io.write_to_dx, g["vol"], (3, 4, 5), [-1.0, -0.5, 0.25], np.diag([0.5, 0.25, 0.125]), "nm") == str(g["dx"])
+    with open(f, "w") as fp:
+        fp.write(str(g["plumed_text"]))
+    names, data = io.read_from_plumedprint(f)
+    assert list(names) == list(g["plumed_names"])
+    assert data.dtype == np.float32 and np.array_equal(data, g["plumed_data"])
