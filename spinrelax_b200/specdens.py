@@ -162,7 +162,7 @@ def A_coefficients_symmtop(v, bProlate=True):
     v = np.asarray(v)
     z2 = np.square(v.take(-1 if bProlate else 0, axis=-1))
     omz = 1 - z2
-    return np.stack((3.0 * z2 * omz, 0.75 * np.square(omz), 0.25 * np.square(3.0 * z2 - 1.0)), axis=-1)
+    return np.stack((3.0 * (z2 * omz), 0.75 * np.square(omz), 0.25 * np.square(3.0 * z2 - 1.0)), axis=-1)   # same rounding order
 
 
 def _do_Jsum(om, A_J, D_J):

@@ -252,6 +252,47 @@ def golden_io():
          **{k: np.array(v) for k, v in out.items()})
 
 
+def golden_sd_host():
+    """Host-only parts of the REAL spectral_densities.py: gyromagnetic data, angular frequencies and prefactors,
+    axisymmetric D / A coefficients, histogram -> bin vectors."""
+    sd = ref_loader.module("spectral_densities")
+    rng = np.random.default_rng(synth.BASE_SEED + 61)
+    out = {}
+    with quiet():
+        cases = [("15N", "1H", 600.13, "MHz", "ps"), ("13C", "1H", 18.8, "T", "ns"), ("15N", "1H", 8.5e8, "Hz", "s")]
+        for k, (a, b, f, fu, tu) in enumerate(cases):
+            w = sd.angularFrequencies(a, b, f, fu, tu)
+            out["w%d_omega" % k] = np.array(w.omega)
+            out["w%d_scalars" % k] = np.array([w.get_factor_DD(), w.get_factor_CSA(), w.get_magnetic_field("T"),
+                                               w.get_magnetic_field("MHz"), w.gA.gamma, w.gB.gamma, w.gA.csa])
+            w.set_time_unit("ns")
+            out["w%d_omega_ns" % k] = np.array(w.omega)
+        w = sd.angularFrequencies("15N", "1H", 600, "MHz", "ps")
+        w.initialise_CSA_array(4, [-160e-6, -170e-6, -175e-6, -180e-6])
+        out["multi_csa_factors"] = np.array(w.get_factor_CSA())
+        out["multi_csa_one"] = np.array(w.get_factor_CSA(2))
+        vecs = rng.standard_normal((5, 7, 3))
+        vecs /= np.linalg.norm(vecs, axis=-1, keepdims=True)
+        for tag, D, conv in (("prolate", [2.5e-5, 1.6], False), ("oblate", [2.5e-5, 0.7], False), ("conv", [3.1e-5, 2.2e-5], True)):
+            r = sd.globalRotationalDiffusion_Axisymmetric(D=D, bConvert=conv)
+            r.vecXH = vecs
+            r.update_A_coefficients()
+            out[tag + "_D"] = np.array(r.D)
+            out[tag + "_DJ"] = np.array(r.get_D_coefficients())
+            out[tag + "_AJ"] = np.array(r.get_A_coefficients())
+            out[tag + "_AJ_ind"] = np.array(r.get_A_coefficients(3))
+            out[tag + "_Dpp"] = np.array(r.transform_D())
+        r = sd.globalRotationalDiffusion_Axisymmetric(tau=8.0e3, aniso=1.3)
+        r.set_Diso(2.2e-5); r.set_Daniso(0.9)
+        out["setter_DJ"] = np.array(r.get_D_coefficients())
+        hist = rng.integers(0, 9, (3, 8, 4)).astype(float)
+        edges = np.empty(2, dtype=object)
+        edges[0], edges[1] = np.linspace(-np.pi, np.pi, 9), np.linspace(-1, 1, 5)
+        bv, bw = sd.convert_LambertCylindricalHist_to_vecs(hist, edges)
+        out["bin_vecs"], out["bin_weights"] = np.array(bv), np.array(bw)
+    save("sd_host.npz", vecs=vecs, hist=hist, edges_phi=edges[0], edges_cos=edges[1], **out)
+
+
 def golden_dq(refdq):
     q = synth.quaternion_walk(6000, seed=synth.BASE_SEED + 31, sigma=(0.01, 0.015, 0.03))     # float32 (G2)
     lags = [5, 10, 40, 100, 333, 1000, 2999]
@@ -546,6 +587,7 @@ def main():
     golden_rtp()
     golden_qs()
     golden_io()
+    golden_sd_host()
     golden_dq(refdq)
     golden_dq_multi(refdq)
     golden_fit()

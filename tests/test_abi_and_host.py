@@ -241,3 +241,40 @@ def test_text_writers_and_readers_match_reference(golden, tmp_path):
     names, data = io.read_from_plumedprint(f)
     assert list(names) == list(g["plumed_names"])
     assert data.dtype == np.float32 and np.array_equal(data, g["plumed_data"])
+
+
+def test_spectral_density_host_objects_match_reference(golden):
+    """gyromagnetic data, angular frequencies / prefactors, axisymmetric D and A coefficients, histogram -> bin
+    vectors: the parts of specdens.py that never touch the GPU, against the real spectral_densities.py."""
+    from spinrelax_b200 import specdens as sd
+    g = golden("sd_host.npz")
+    cases = [("15N", "1H", 600.13, "MHz", "ps"), ("13C", "1H", 18.8, "T", "ns"), ("15N", "1H", 8.5e8, "Hz", "s")]
+    for k, (a, b, f, fu, tu) in enumerate(cases):
+        w = sd.angularFrequencies(a, b, f, fu, tu)
+        assert np.array_equal(w.omega, g["w%d_omega" % k])
+        sc = np.array([w.get_factor_DD(), w.get_factor_CSA(), w.get_magnetic_field("T"), w.get_magnetic_field("MHz"),
+                       w.gA.gamma, w.gB.gamma, w.gA.csa])
+        assert np.allclose(sc, g["w%d_scalars" % k], rtol=1e-15, atol=0)
+        w.set_time_unit("ns")
+        assert np.allclose(w.omega, g["w%d_omega_ns" % k], rtol=1e-15, atol=0)
+    w = sd.angularFrequencies("15N", "1H", 600, "MHz", "ps")
+    w.initialise_CSA_array(4, [-160e-6, -170e-6, -175e-6, -180e-6])
+    assert np.allclose(w.get_factor_CSA(), g["multi_csa_factors"], rtol=1e-15)
+    assert np.allclose(w.get_factor_CSA(2), g["multi_csa_one"], rtol=1e-15)
+    for tag, D, conv in (("prolate", [2.5e-5, 1.6], False), ("oblate", [2.5e-5, 0.7], False), ("conv", [3.1e-5, 2.2e-5], True)):
+        r = sd.globalRotationalDiffusion_Axisymmetric(D=D, bConvert=conv)
+        r.vecXH = g["vecs"]
+        r.update_A_coefficients()
+        assert np.array_equal(r.D, g[tag + "_D"]) and np.array_equal(r.get_D_coefficients(), g[tag + "_DJ"])
+        assert np.array_equal(r.get_A_coefficients(), g[tag + "_AJ"])
+        assert np.array_equal(r.get_A_coefficients(3), g[tag + "_AJ_ind"])
+        assert np.array_equal(np.array(r.transform_D()), g[tag + "_Dpp"])
+    r = sd.globalRotationalDiffusion_Axisymmetric(tau=8.0e3, aniso=1.3)
+    r.set_Diso(2.2e-5); r.set_Daniso(0.9)
+    assert np.array_equal(r.get_D_coefficients(), g["setter_DJ"])
+    edges = np.empty(2, dtype=object)
+    edges[0], edges[1] = g["edges_phi"], g["edges_cos"]
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        bv, bw = sd.convert_LambertCylindricalHist_to_vecs(g["hist"], edges)
+    assert np.array_equal(bv, g["bin_vecs"]) and np.array_equal(bw, g["bin_weights"])
