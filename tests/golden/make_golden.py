@@ -506,6 +506,27 @@ def golden_relax_cli():
          **{"expt_" + k: np.array(v) for k, v in expt.items()})
 
 
+def golden_fit_cli():
+    """calculate-fitted-Ct.py run unmodified on a `_Ctint.dat` file: default ladder, --nc 2, --nofast."""
+    import subprocess
+    import tempfile
+    gs = ref_loader.module("general_scripts")
+    g = np.load(os.path.join(OUT, "fit.npz"))
+    t, Ct, dCt = g["t"], g["Ct"], g["dCt"]
+    out = {}
+    with tempfile.TemporaryDirectory() as td:
+        with quiet():
+            gs.print_sxylist(td + "/c_Ctint.dat", list(range(1, len(Ct) + 1)), t,
+                             np.stack((Ct.astype(np.float32), dCt.astype(np.float32)), axis=-1))
+        out["ctint"] = open(td + "/c_Ctint.dat").read()
+        env = dict(os.environ, PYTHONPATH=os.pathsep.join([ref_loader.STUBS, ref_loader.REF_BUILD, ref_loader.REFERENCE]))
+        for tag, extra in (("ladder", []), ("nc2", ["--nc", "2"]), ("nofast", ["--nofast"])):
+            cmd = [sys.executable, ref_loader.REFERENCE + "/calculate-fitted-Ct.py", "-f", td + "/c_Ctint.dat", "-o", td + "/" + tag] + extra
+            subprocess.run(cmd, env=env, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            out[tag] = open(td + "/%s_fittedCt.dat" % tag).read()
+    save("fit_cli.npz", **{k: np.array(v) for k, v in out.items()})
+
+
 def golden_relax_opt():
     """calculate-relaxations-multi-field.py --opt ... (Powell optimisation against experiment, spectral_densities.py
     :1302-1447) run unmodified.  The "experiments" are the reference's own predictions at perturbed parameters
@@ -593,6 +614,7 @@ def main():
     golden_fit()
     golden_relax()
     golden_relax_cli()
+    golden_fit_cli()
     golden_relax_opt()
 
 
