@@ -105,6 +105,48 @@ def golden_traj(refct):
          fit=sel["custom occupancy"], vecXH=vec)
 
 
+def golden_ct_cli(refct=None):
+    """The output files of calculate-Ct-from-traj.py for `--tau --Ct --vecAvg --S2 --vecHist --binary --vecRot q`,
+    produced by chaining the REAL functions and writers exactly as its __main__ does (:514-646; the script itself
+    needs mdtraj to load a trajectory).  Two trajectories of unequal length, fitted and unfitted vectors."""
+    import tempfile
+    refct = refct or ref_loader.script("calculate-Ct-from-traj.py")
+    qs = ref_loader.module("transforms3d_supplement")
+    gs = ref_loader.module("general_scripts")
+    gm = ref_loader.module("general_maths")
+    q = np.array([0.83, -0.31, 0.22, 0.41]); q = q / np.linalg.norm(q)
+    dt, tau, zeta = 10.0, 600.0, (1.02 / 1.04) ** 6
+    fitA, fitB = synth.nh_vectors(190, 4, seed=synth.BASE_SEED + 71), synth.nh_vectors(131, 4, seed=synth.BASE_SEED + 72)
+    tum = synth.quaternion_walk(190, seed=synth.BASE_SEED + 73, sigma=(0.02, 0.02, 0.02)).astype(np.float64)
+    extA = np.array([qs.rotate_vector_simd(fitA[i].astype(np.float64), tum[i]) for i in range(190)]).astype(np.float32)
+    extB = np.array([qs.rotate_vector_simd(fitB[i].astype(np.float64), tum[i]) for i in range(131)]).astype(np.float32)
+    names = [3, 4, 7, 9]
+    out = {}
+    with tempfile.TemporaryDirectory() as td, quiet(), np.errstate(all="ignore"):
+        vecXH = refct.reformat_vecs_by_tau([extA, extB], dt, tau)
+        vecXHfit = refct.reformat_vecs_by_tau([fitA, fitB], dt, tau)
+        tt = refct.calculate_dt(dt, tau)
+        Ct, dCt = refct.calculate_Ct_Palmer(vecXH)
+        gs.print_sxylist(td + "/Ctext", names, tt, np.stack((Ct.T, dCt.T), axis=-1)); out["Ctext"] = open(td + "/Ctext").read()
+        Ct, dCt = refct.calculate_Ct_Palmer(vecXHfit)
+        gs.print_sxylist(td + "/Ctint", names, tt, np.stack((Ct.T, dCt.T), axis=-1)); out["Ctint"] = open(td + "/Ctint").read()
+        sh = vecXHfit.shape
+        v3 = vecXHfit.reshape((sh[0] * sh[1], sh[-2], sh[-1]))
+        v3 = qs.rotate_vector_simd(v3, q)
+        avg = gs.normalise_vector_array(np.mean(v3, axis=0))
+        gs.print_xylist(td + "/avg", names, np.array(avg).T, True); out["avgvec"] = open(td + "/avg").read()
+        rtp = np.transpose(gm.xyz_to_rtp(v3), axes=(1, 0, 2))
+        rtp = np.delete(rtp, 0, axis=2)
+        rtp[..., 1] = np.cos(rtp[..., 1])
+        hl = np.zeros((4, 72, 36), dtype=rtp.dtype)
+        for i in range(4):
+            hl[i], edges = np.histogramdd(rtp[i], bins=(72, 36), range=((-np.pi, np.pi), (-1, 1)))
+        S2 = refct.calculate_S2_by_outerProduct(v3, dt, tau)
+        gs.print_xylist(td + "/S2", names, (S2.T) * zeta, True); out["S2"] = open(td + "/S2").read()
+    save("ct_cli.npz", q=q, fitA=fitA, fitB=fitB, extA=extA, extB=extB, names=np.array(names), hist=hl.astype(np.int64),
+         edges_phi=edges[0], edges_cos=edges[1], **{k: np.array(v) for k, v in out.items()})
+
+
 def golden_hist(refct):
     qs = ref_loader.module("transforms3d_supplement")
     gm = ref_loader.module("general_maths")
@@ -604,6 +646,7 @@ def main():
     refdq = ref_loader.script("calculate-dq-distribution.py")
     golden_ct(refct)
     golden_traj(refct)
+    golden_ct_cli(refct)
     golden_hist(refct)
     golden_rtp()
     golden_qs()

@@ -278,3 +278,26 @@ def test_spectral_density_host_objects_match_reference(golden):
     with contextlib.redirect_stdout(io.StringIO()):
         bv, bw = sd.convert_LambertCylindricalHist_to_vecs(g["hist"], edges)
     assert np.array_equal(bv, g["bin_vecs"]) and np.array_equal(bw, g["bin_weights"])
+
+
+def test_ct_cli_argument_errors_need_no_gpu(tmp_path):
+    """Exit codes of calculate-Ct-from-traj.py's argument checks (:358-360, :372-375, :411-414, tau vs dt)."""
+    import contextlib, io
+    from spinrelax_b200 import cli_ct
+    v = np.zeros((40, 3, 3), dtype=np.float32)
+    v[..., 2] = 1.0
+    np.savez(tmp_path / "v.npz", vecs=v, dt=10.0)
+    fn = str(tmp_path / "v.npz")
+
+    def code(argv):
+        with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+            with pytest.raises(SystemExit) as e:
+                cli_ct.main(argv)
+        return e.value.code
+
+    assert code(["-f", fn, "-o", str(tmp_path / "o"), "--Ct"]) == 1                                  # --Ct without --tau
+    assert code(["-f", fn, "-o", str(tmp_path / "o"), "--vecRot", "1 0 0"]) == 23                    # 3 numbers
+    assert code(["-f", fn, "-o", str(tmp_path / "o"), "--vecRot", "1 1 0 0"]) == 23                  # not a unit quaternion
+    assert code(["-f", fn, fn, "-s", fn, fn, fn, "-o", str(tmp_path / "o")]) == 1                    # refs != trajectories
+    assert code(["-f", fn, "-o", str(tmp_path / "o"), "--Ct", "--tau", "15"]) == 1                   # dt > tau / 2
+    assert code(["-f", str(tmp_path / "v.xtc"), "-o", str(tmp_path / "o")]) == 2                     # mdtraj formats: out of scope
