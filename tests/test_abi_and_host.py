@@ -301,3 +301,34 @@ def test_ct_cli_argument_errors_need_no_gpu(tmp_path):
     assert code(["-f", fn, fn, "-s", fn, fn, fn, "-o", str(tmp_path / "o")]) == 1                    # refs != trajectories
     assert code(["-f", fn, "-o", str(tmp_path / "o"), "--Ct", "--tau", "15"]) == 1                   # dt > tau / 2
     assert code(["-f", str(tmp_path / "v.xtc"), "-o", str(tmp_path / "o")]) == 2                     # mdtraj formats: out of scope
+
+
+def test_host_reshaping_properties():
+    """Property tests (hypothesis) of the host helpers that decide which samples enter which block / lag."""
+    from hypothesis import given, settings, strategies as st
+    from oracle import dq_oracle
+    from spinrelax_b200 import ct, dq
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.lists(st.integers(1, 90), min_size=1, max_size=4), st.integers(2, 40), st.integers(1, 5))
+    def reformat(lengths, nF, nR):
+        rng = np.random.default_rng(sum(lengths) + nF)
+        trajs = [rng.standard_normal((n, nR, 3)).astype(np.float32) for n in lengths]
+        dt, tau = 2.0, 2.0 * nF
+        if all(n < nF for n in lengths):
+            return                                    # no complete block: the reference fails on the empty reshape
+        a = ct.reformat_vecs_by_tau(trajs, dt, tau)
+        b = ct_oracle.reformat_by_tau(trajs, dt, tau)
+        assert a.dtype == b.dtype and np.array_equal(a, b)
+        assert a.shape == (sum(n // nF for n in lengths), nF, nR, 3)
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(20, 400), st.floats(0.0, 40.0), st.floats(0.0, 30.0), st.floats(50.0, 3000.0))
+    def lags(n, min_dt, skip_dt, max_dt):
+        times = np.arange(n) * 10.0
+        lo, hi, step, ddt = dq.lag_grid(times, min_dt, max_dt, skip_dt)
+        ref_lags, ref_ddt = dq_oracle.lag_grid(times, min_dt, max_dt, skip_dt)
+        assert list(range(lo, hi + 1, step)) == ref_lags and ddt == ref_ddt
+
+    reformat()
+    lags()
