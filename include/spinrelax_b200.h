@@ -4,7 +4,7 @@
  * Drop-in boundary for the trajectory-analysis hot path of zharmad/SpinRelax.  The reference has no
  * FFI for this path except the `npufunc.Jomega` ufunc (Jomega/Jomega.c:49-66); everything else is
  * NumPy inside the stage scripts.  Each entry point below names the reference function (file:line in
- * the SpinRelax tree) whose arithmetic it replaces.  The Python host mirror (spinrelax_b200/*.py)
+ * the SpinRelax tree) whose arithmetic it replaces.  The Python host mirror (the .py files of spinrelax_b200/)
  * binds these with ctypes; INTEGRATION.md shows the stub a SpinRelax maintainer would add.
  *
  * Conventions
