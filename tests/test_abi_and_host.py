@@ -332,3 +332,44 @@ def test_host_reshaping_properties():
 
     reformat()
     lags()
+
+
+def test_ctypes_prototypes_match_the_header():
+    """Every prototype in _lib.py has the parameter count and parameter kinds (pointer / int / long long / size_t /
+    double) and the return kind of the declaration in include/spinrelax_b200.h."""
+    from spinrelax_b200 import _lib
+    lib = _lib.load()
+    hdr = open(os.path.join(ROOT, "include", "spinrelax_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", " ", hdr, flags=re.S)
+    decls = re.findall(r"\b(int|void|long long|size_t|const char\s*\*)\s+(sr_\w+)\s*\(([^;{]*)\)\s*;", hdr)
+    assert len(decls) >= 30
+
+    def kind_of_c(p):
+        p = p.strip()
+        if p in ("void", ""):
+            return None
+        if "*" in p:
+            return "ptr"
+        t = " ".join(p.split()[:-1]).replace("const", "").strip()
+        return {"int": "int", "long long": "ll", "size_t": "size", "double": "double", "unsigned int": "int"}[t]
+
+    def kind_of_ctypes(t):
+        if t is None:
+            return None
+        if t in (ctypes.c_void_p, ctypes.c_char_p) or hasattr(t, "contents") or issubclass(t, ctypes._Pointer):
+            return "ptr"
+        return {ctypes.c_int: "int", ctypes.c_longlong: "ll", ctypes.c_size_t: "size", ctypes.c_double: "double"}[t]
+
+    checked = 0
+    for ret, name, params in decls:
+        fn = getattr(lib, name)
+        want = [k for k in (kind_of_c(p) for p in params.replace("\n", " ").split(",")) if k is not None]
+        got = [kind_of_ctypes(t) for t in (fn.argtypes or [])]
+        # c_size_t and c_longlong / c_ulong may alias on LP64: compare by size class
+        norm = lambda ks: ["ll" if k == "size" else k for k in ks]      # noqa: E731
+        assert norm(got) == norm(want), (name, got, want)
+        rk = "ptr" if "*" in ret else {"int": "int", "void": None, "long long": "ll", "size_t": "ll"}[ret]
+        gk = kind_of_ctypes(fn.restype)
+        assert ("ll" if gk == "size" else gk) == rk, (name, gk, rk)
+        checked += 1
+    assert checked == len(decls)
