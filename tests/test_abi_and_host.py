@@ -373,3 +373,28 @@ def test_ctypes_prototypes_match_the_header():
         assert ("ll" if gk == "size" else gk) == rk, (name, gk, rk)
         checked += 1
     assert checked == len(decls)
+
+
+def test_call_sites_pass_as_many_arguments_as_the_header_declares():
+    """AST scan of the host package: every `lib.sr_*(...)` / `getattr(lib, fn)(...)`-style call with a literal entry
+    point name passes exactly the number of arguments its C declaration has."""
+    import ast
+    hdr = open(os.path.join(ROOT, "include", "spinrelax_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", " ", hdr, flags=re.S)
+    nparams = {}
+    for _, name, params in re.findall(r"\b(int|void|long long|size_t|const char\s*\*)\s+(sr_\w+)\s*\(([^;{]*)\)\s*;", hdr):
+        ps = [p.strip() for p in params.replace("\n", " ").split(",")]
+        nparams[name] = 0 if ps in ([""], ["void"]) else len(ps)
+    calls = 0
+    pkg = os.path.join(ROOT, "spinrelax_b200")
+    for fn in sorted(os.listdir(pkg)) + ["../bench.py", "../bench_secondary.py", "../bench_multi.py", "../__graft_entry__.py"]:
+        if not fn.endswith(".py"):
+            continue
+        tree = ast.parse(open(os.path.join(pkg, fn)).read())
+        for node in ast.walk(tree):
+            if isinstance(node, ast.Call) and isinstance(node.func, ast.Attribute) and node.func.attr in nparams:
+                if any(isinstance(a, ast.Starred) for a in node.args):
+                    continue
+                assert len(node.args) == nparams[node.func.attr], (fn, node.lineno, node.func.attr)
+                calls += 1
+    assert calls >= 25
