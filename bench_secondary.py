@@ -119,7 +119,7 @@ def bench_fit_relax(quick):
                       "500-point curves, host selection logic included)", "n_gpus": 1, "ms_per_step": fit_s * 1e3,
                       "config": {"workload": "c5 fits: %d residues x 500-point C(t)" % nR}, "dtype": "f64",
                       "kernel_ms": kern_ms, "kernel_only_residues_per_s": nR / (kern_ms * 1e-3),
-                      "note": "ct_fit_lm_kernel time summed over the five rungs; the rest of ms_per_step is the reference's "
+                      "note": "ct_fit_trf_kernel time summed over the five rungs; the rest of ms_per_step is the reference's "
                               "per-residue selection ladder on the host (fitting_Ct_functions.py:278-304)",
                       "data": "synthetic", "roofline": None,
                       "cpu_baseline": {"value": cpu_fit, "unit": "residues/s", "cores": 1, "kind": "port",

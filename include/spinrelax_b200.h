@@ -29,7 +29,7 @@ extern "C" {
 #define SR_ERR_WORKSPACE (-3)
 #define SR_ERR_OVERFLOW (-4)
 
-#define SR_ABI_VERSION 1
+#define SR_ABI_VERSION 2
 
 /* library / device introspection */
 int sr_abi_version(void);
@@ -229,16 +229,25 @@ int sr_relax_eval(int iso, const double* h_D_J, double zeta, double time_fact, d
 
 /* ------------------------------------------------------------------------------------------------
  * K5: batched bounded least-squares fit of C(t) = S2 + sum_i C_i exp(-t/tau_i), one CTA per residue.
- * Replaces the scipy curve_fit call in autoCorrelationModel.conduct_curve_fitting,
+ * Replaces the scipy.optimize.curve_fit call in autoCorrelationModel.conduct_curve_fitting,
  * fitting_Ct_functions.py:322-324 (model :419-427, bounds :412-416, initial guess :359-374 built by caller).
+ * The solver is the algorithm curve_fit runs when bounds are given -- least_squares(method='trf', tr_solver='exact',
+ * x_scale=1) -- restated step for step (csrc/trf_core.cuh), because the reference's model selection depends on where
+ * that solver stops and on whether it reports success (:325-328).
  * d_t, d_y, d_sigma: (nR, L) float64 (d_sigma may be NULL = unweighted).  Parameters ordered as the
  * reference: C_1..C_nc, tau_1..tau_nc [, S2]; d_p0, d_lo, d_hi, d_popt are (nR, nParams).
- * d_JtJ (nR, nParams, nParams) = J^T J of the sigma-weighted residuals at the optimum, d_cost (nR) =
- * 0.5 sum r^2, d_status (nR, 2) = {1 ftol | 2 step below precision | 3 damping overflow | 0 max_iter, iterations}.
+ * max_nfev <= 0 selects SciPy's default 100*nParams; ftol = xtol = gtol = 1e-8 are curve_fit's values.
+ * d_R (nR, nParams, nParams): upper-triangular R factor of the sigma-weighted Jacobian at the solution (same singular
+ * values and right singular vectors as the Jacobian curve_fit decomposes for pcov); d_cost (nR) = 0.5 sum r^2;
+ * d_status (nR, 2) = {SciPy termination status, nfev}: 1 gtol, 2 ftol, 3 xtol, 4 ftol and xtol, 0 max_nfev reached
+ * (curve_fit raises RuntimeError), -3 p0 outside the bounds, -4 residuals not finite at p0 (both ValueError upstream).
+ * Curves too long for shared memory need d_work of sr_ct_fit_workspace_bytes() bytes (0 = not needed).
  * ---------------------------------------------------------------------------------------------- */
-int sr_ct_fit_lm(const double* d_t, const double* d_y, const double* d_sigma, int nR, long long L, int nParams,
-                 const double* d_p0, const double* d_lo, const double* d_hi, int max_iter, double ftol,
-                 double* d_popt, double* d_JtJ, double* d_cost, int* d_status, void* stream);
+size_t sr_ct_fit_workspace_bytes(int nR, long long L, int nParams);
+int sr_ct_fit_trf(const double* d_t, const double* d_y, const double* d_sigma, int nR, long long L, int nParams,
+                  const double* d_p0, const double* d_lo, const double* d_hi, int max_nfev, double ftol, double xtol,
+                  double gtol, double* d_popt, double* d_R, double* d_cost, int* d_status, void* d_work,
+                  size_t work_bytes, void* stream);
 
 #ifdef __cplusplus
 }

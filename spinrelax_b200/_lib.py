@@ -10,6 +10,7 @@ from . import build as _build
 
 _c = ctypes
 _LIB = None
+ABI_VERSION = 2
 
 
 class SpinRelaxError(RuntimeError):
@@ -44,7 +45,9 @@ def _declare(lib):
         "sr_relax_a_moments": (i, [vp, i, vp, i, i, vp, vp]),
         "sr_relax_eval": (i, [i, dp, _c.c_double, _c.c_double, _c.c_double, _c.c_double, _c.c_double, i, i, i, i, i,
                               vp, vp, vp, vp, vp, vp, vp, vp, vp]),
-        "sr_ct_fit_lm": (i, [vp, vp, vp, i, ll, i, vp, vp, vp, i, _c.c_double, vp, vp, vp, vp, vp]),
+        "sr_ct_fit_workspace_bytes": (sz, [i, ll, i]),
+        "sr_ct_fit_trf": (i, [vp, vp, vp, i, ll, i, vp, vp, vp, i, _c.c_double, _c.c_double, _c.c_double, vp, vp, vp, vp,
+                              vp, sz, vp]),
         "sr_dq_moments": (i, [vp, ll, vp, i, ll, i, vp, vp]),
         "sr_dq_moments_pooled": (i, [vp, ll, vp, i, ll, i, i, i, i, vp, vp]),
         "sr_dq_self": (i, [vp, ll, ll, vp, vp]),
@@ -71,12 +74,13 @@ def load():
     global _LIB
     if _LIB is not None:
         return _LIB
-    path = _build.LIB
-    if not os.path.exists(path):
-        _build.build()
+    # build() compares the digest of csrc/ + the header with the stamp next to the .so and returns at once when they
+    # match; after an edit it recompiles, so a stale binary is never loaded.  On a box without nvcc (the .so travels
+    # with the snapshot) a matching stamp is required.
+    path = _build.build()
     lib = _c.CDLL(path)
     _declare(lib)
-    if lib.sr_abi_version() != 1:
+    if lib.sr_abi_version() != ABI_VERSION:
         raise SpinRelaxError("libspinrelax_b200.so ABI version mismatch")
     _LIB = lib
     return lib

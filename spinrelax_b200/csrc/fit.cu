@@ -1,235 +1,314 @@
-// K5: batched bounded Levenberg-Marquardt fit of C(t) = S2 + sum_i C_i exp(-t/tau_i), one CTA per residue.
+// K5: batched bounded least-squares fit of C(t) = S2 + sum_i C_i exp(-t/tau_i), one CTA per residue.
 // Replaces the scipy.optimize.curve_fit call of autoCorrelationModel.conduct_curve_fitting
 // (fitting_Ct_functions.py:306-345; model curvefit_exponential :419-427; bounds :412-416).
-// Parameter vector as in the reference: p = (C_1..C_nc, tau_1..tau_nc [, S2]); with an even count
-// S2 = 1 - sum C.  Residuals are (model - y)/sigma (curve_fit with sigma, absolute_sigma=False).
-// The kernel returns the optimum, the Gauss-Newton matrix J^T J at the optimum (the host forms pcov from
-// it the way SciPy does from the SVD of J) and the cost 0.5 sum r^2.  Model selection (the 2,3,5,7,9
-// ladder, chi^2 ratio, over-fitting flags) stays in Python, verbatim (fitct.py).
+//
+// The reference's model-selection ladder (:278-304) depends on *where SciPy's solver stops* and on whether it
+// reports success (a RuntimeError from curve_fit is swallowed at :325-328 and ends the ladder), so the kernel runs
+// the same algorithm as SciPy's least_squares(method='trf', tr_solver='exact', x_scale=1, ftol=xtol=gtol=1e-8,
+// max_nfev=100 n): see trf_core.cuh for the solver logic (one thread) and fit_model.cuh for the model arithmetic.
+// This file holds the O(L) parts, done by the whole CTA:
+//   * residuals (1/sigma)(f - y) and the analytic Jacobian, written column-major into the work matrix A (shared
+//     memory when the curve fits, a global workspace otherwise), with the gradient J^T f and the cost block-reduced
+//     in the same pass;
+//   * Householder QR of the augmented Jacobian [J d; diag(sqrt(diag_h))] with the residuals as an extra column:
+//     one block reduction per column (the sums of A[:,k] . A[:,j] for all j >= k give the column norm and every
+//     v^T A[:,j] at once), each thread updating the rows it owns -- 9 barriers for a 9-parameter fit;
+//   * at the solution, the QR of the unscaled Jacobian: its R factor has the singular values and right vectors of
+//     J, from which the host forms pcov exactly as curve_fit does from svd(J).
 #include "common.cuh"
+#include "fit_model.cuh"
 
 namespace {
 
 constexpr int kMaxP = 9;
-constexpr int kNRed = kMaxP * (kMaxP + 1) / 2 + kMaxP + 1;   // packed JtJ + Jtr + cost
 constexpr int kFitThreads = 128;
+constexpr int kFitWarps = kFitThreads / 32;
+constexpr size_t kFitSmemLimit = 200 * 1024;
 
+enum : int { kFlagStop = 0, kFlagQR = 1, kFlagTrial = 2, kFlagAccept = 3, kFlagReject = 4 };
+
+template <int N>
 struct FitShared {
-  double p[kMaxP], ptry[kMaxP], lo[kMaxP], hi[kMaxP];
-  double JtJ[kMaxP * kMaxP], Jtr[kMaxP], cost;
-  double tJtJ[kMaxP * kMaxP], tJtr[kMaxP], tcost;
-  double red[kFitThreads / 32][kNRed];
-  int flag, trunc;
+  srtrf::Core<N> core;
+  double red[2][kFitWarps][N + 2];
+  double qtf[N];
+  int flag;
 };
 
-// accumulate cost, J^T r and J^T J of the model at parameters q over this thread's points, then block-reduce
-template <int nP>
-__device__ void evaluate(const double* __restrict__ t, const double* __restrict__ y, const double* __restrict__ sig,
-                         int L, const double* q, FitShared& sh, double* outJtJ, double* outJtr, double* outCost) {
-  constexpr int nc = nP / 2;
-  constexpr bool free_s2 = (nP & 1);
-  double C[4], itau[4];
-  double sumC = 0.0;
-#pragma unroll
-  for (int i = 0; i < nc; ++i) { C[i] = q[i]; itau[i] = 1.0 / q[nc + i]; sumC += C[i]; }   // one division per tau, not per point
-  const double S2 = free_s2 ? q[nP - 1] : 1.0 - sumC;
-  constexpr int nUsed = nP * (nP + 1) / 2 + nP + 1;
-  double acc[nUsed];
-#pragma unroll
-  for (int i = 0; i < nUsed; ++i) acc[i] = 0.0;
-  for (int k = threadIdx.x; k < L; k += kFitThreads) {
-    const double tk = t[k];
-    const double w = sig ? 1.0 / sig[k] : 1.0;
-    double g[nP];
-    double f = S2;
-#pragma unroll
-    for (int i = 0; i < nc; ++i) {
-      const double e = exp(-tk * itau[i]);
-      f += C[i] * e;
-      g[i] = (e - (free_s2 ? 0.0 : 1.0)) * w;
-      g[nc + i] = C[i] * e * tk * (itau[i] * itau[i]) * w;
-    }
-    if (free_s2) g[nP - 1] = w;
-    const double r = (f - y[k]) * w;
-    int m = 0;
-#pragma unroll
-    for (int a = 0; a < nP; ++a)
-#pragma unroll
-      for (int b = a; b < nP; ++b) acc[m++] += g[a] * g[b];
-#pragma unroll
-    for (int a = 0; a < nP; ++a) acc[m++] += g[a] * r;
-    acc[m] += 0.5 * r * r;
-  }
+// block-wide sum of NV per-thread values; every thread gets all NV totals.  `parity` alternates between calls so
+// that one barrier per reduction is enough.
+template <int N, int NV>
+__device__ __forceinline__ void block_sum(double* acc, FitShared<N>& sh, int& parity) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-  for (int i = 0; i < nUsed; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const double v = sr_warp_sum(acc[i]);
-    if (lane == 0) sh.red[warp][i] = v;
+    if (lane == 0) sh.red[parity][warp][i] = v;
   }
   __syncthreads();
-  // one thread per reduced quantity combines the warps' partial sums (the solver iterates one residue per CTA, so
-  // the time of a fit is the latency of this chain, not its throughput)
-  if (threadIdx.x < nUsed) {
-    const int m = threadIdx.x;
-    double s2 = 0.0;
 #pragma unroll
-    for (int w2 = 0; w2 < kFitThreads / 32; ++w2) s2 += sh.red[w2][m];
-    constexpr int nTri = nP * (nP + 1) / 2;
-    if (m < nTri) {
-      int a = 0, rem = m;                      // m -> (a, b >= a) of the packed upper triangle
-      while (rem >= nP - a) { rem -= nP - a; ++a; }
-      const int b = a + rem;
-      outJtJ[a * nP + b] = s2; outJtJ[b * nP + a] = s2;
-    } else if (m < nTri + nP) {
-      outJtr[m - nTri] = s2;
-    } else {
-      *outCost = s2;
-    }
+  for (int i = 0; i < NV; ++i) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < kFitWarps; ++w) s += sh.red[parity][w][i];
+    acc[i] = s;
   }
-  __syncthreads();
+  parity ^= 1;
 }
 
-// solve (A + lam*diag(A)) d = -g on the free set by Cholesky; returns false if not positive definite
-__device__ bool lm_step(const double* A, const double* g, const bool* fixed, int n, double lam, double* d) {
-  double M[kMaxP * kMaxP], b[kMaxP];
-  int idx[kMaxP], m = 0;
-  for (int i = 0; i < n; ++i) { d[i] = 0.0; if (!fixed[i]) idx[m++] = i; }
-  if (m == 0) return true;
-  for (int i = 0; i < m; ++i) {
-    for (int j = 0; j < m; ++j) M[i * m + j] = A[idx[i] * n + idx[j]];
-    const double dii = A[idx[i] * n + idx[i]];
-    M[i * m + i] += lam * (dii > 0.0 ? dii : 1.0);
-    b[i] = -g[idx[i]];
+template <int N>
+struct Problem {
+  const double* t; const double* y; const double* w;     // w = 1/sigma (shared-memory copy) or nullptr
+  const double* sig;                                       // global sigma, used when w == nullptr
+  int L;
+  __device__ __forceinline__ double weight(int k) const { return w ? w[k] : (sig ? 1.0 / sig[k] : 1.0); }
+};
+
+// residuals and Jacobian at x into A (column-major, pitch Mp; column N = residuals); returns cost, fills g
+template <int N>
+__device__ void eval_jac(const Problem<N>& pb, const double* x, double* A, int Mp, FitShared<N>& sh, int& parity,
+                         double* g, double& cost) {
+  srfit::ModelPars<N> mp;
+  srfit::prepare<N>(x, mp);
+  double acc[N + 1];
+#pragma unroll
+  for (int i = 0; i <= N; ++i) acc[i] = 0.0;
+  for (int k = threadIdx.x; k < pb.L; k += kFitThreads) {
+    double row[N];
+    const double r = srfit::residual_and_row<N>(mp, pb.t[k], pb.y[k], pb.weight(k), row);
+#pragma unroll
+    for (int i = 0; i < N; ++i) { A[(size_t)i * Mp + k] = row[i]; acc[i] += row[i] * r; }
+    A[(size_t)N * Mp + k] = r;
+    acc[N] += r * r;
   }
-  double inv[kMaxP];                           // 1 / L_jj: one rsqrt per column instead of a division per element
-  for (int j = 0; j < m; ++j) {
-    double s = M[j * m + j];
-    for (int k = 0; k < j; ++k) s -= M[j * m + k] * M[j * m + k];
-    if (!(s > 0.0) || !(s < 1e300)) return false;
-    const double rj = rsqrt(s);
-    inv[j] = rj;
-    M[j * m + j] = s * rj;
-    for (int i = j + 1; i < m; ++i) {
-      double v = M[i * m + j];
-      for (int k = 0; k < j; ++k) v -= M[i * m + k] * M[j * m + k];
-      M[i * m + j] = v * rj;
-    }
-  }
-  for (int i = 0; i < m; ++i) {
-    double v = b[i];
-    for (int k = 0; k < i; ++k) v -= M[i * m + k] * b[k];
-    b[i] = v * inv[i];
-  }
-  for (int i = m - 1; i >= 0; --i) {
-    double v = b[i];
-    for (int k = i + 1; k < m; ++k) v -= M[k * m + i] * b[k];
-    b[i] = v * inv[i];
-  }
-  for (int i = 0; i < m; ++i) d[idx[i]] = b[i];
-  return true;
+  block_sum<N, N + 1>(acc, sh, parity);
+#pragma unroll
+  for (int i = 0; i < N; ++i) g[i] = acc[i];
+  cost = 0.5 * acc[N];
 }
 
-template <int nP>
-__global__ void __launch_bounds__(kFitThreads)
-ct_fit_lm_kernel(const double* __restrict__ T, const double* __restrict__ Y, const double* __restrict__ SIG, int L,
-                 const double* __restrict__ P0, const double* __restrict__ LO, const double* __restrict__ HI, int max_iter,
-                 double ftol, double* __restrict__ POPT, double* __restrict__ JTJ, double* __restrict__ COST,
-                 int* __restrict__ STATUS) {
-  __shared__ FitShared sh;
-  const int r = blockIdx.x;
-  const double* t = T + (long long)r * L;
-  const double* y = Y + (long long)r * L;
-  const double* sig = SIG ? SIG + (long long)r * L : nullptr;
-  constexpr int nc = nP / 2;
-  if (threadIdx.x < nP) {
-    const int i = threadIdx.x;
-    double lo = LO[(long long)r * nP + i], hi = HI[(long long)r * nP + i];
-    if (i >= nc && i < 2 * nc) lo = fmax(lo, 1e-12 * hi);     // tau strictly positive (SciPy TRF iterates are interior)
-    sh.lo[i] = lo; sh.hi[i] = hi;
-    const double eps = 1e-10 * (hi - lo);                     // strictly feasible start (scipy make_strictly_feasible)
-    sh.p[i] = fmin(fmax(P0[(long long)r * nP + i], lo + eps), hi - eps);
+template <int N>
+__device__ double eval_cost(const Problem<N>& pb, const double* x, FitShared<N>& sh, int& parity) {
+  srfit::ModelPars<N> mp;
+  srfit::prepare<N>(x, mp);
+  double acc[1] = {0.0};
+  for (int k = threadIdx.x; k < pb.L; k += kFitThreads) {
+    const double r = srfit::residual_and_row<N>(mp, pb.t[k], pb.y[k], pb.weight(k), nullptr);
+    acc[0] += r * r;
   }
-  __syncthreads();
-  evaluate<nP>(t, y, sig, L, sh.p, sh, sh.JtJ, sh.Jtr, &sh.cost);
-  double lam = 1e-3;
-  int status = 0, it = 0, small = 0;
-  for (; it < max_iter; ++it) {
+  block_sum<N, 1>(acc, sh, parity);
+  return 0.5 * acc[0];
+}
+
+// Householder QR of the M x (N+1) matrix A; thread 0 stores R (row major) and the first N entries of Q^T rhs
+template <int N>
+__device__ void block_qr(double* A, int M, int Mp, FitShared<N>& sh, int& parity, double* R, double* qtf) {
+  for (int k = 0; k < N; ++k) {
+    double sums[N + 1];
+#pragma unroll
+    for (int j = 0; j <= N; ++j) sums[j] = 0.0;
+    int i0 = threadIdx.x;
+    while (i0 <= k) i0 += kFitThreads;
+    for (int i = i0; i < M; i += kFitThreads) {
+      const double aik = A[(size_t)k * Mp + i];
+#pragma unroll
+      for (int j = 0; j <= N; ++j)
+        if (j >= k) sums[j] += aik * A[(size_t)j * Mp + i];
+    }
+    block_sum<N, N + 1>(sums, sh, parity);
+    double row[N + 1];
+#pragma unroll
+    for (int j = 0; j <= N; ++j) row[j] = (j >= k) ? A[(size_t)j * Mp + k] : 0.0;
+    srfit::HouseholderCol<N> h;
+    srfit::householder_column<N>(k, row, sums, h);
     if (threadIdx.x == 0) {
-      // active set: a parameter sitting on a bound with the gradient pushing outwards is frozen
-      bool fixed[kMaxP];
-      for (int i = 0; i < nP; ++i) {
-        const double span = sh.hi[i] - sh.lo[i];
-        const bool at_lo = sh.p[i] - sh.lo[i] <= 1e-12 * span, at_hi = sh.hi[i] - sh.p[i] <= 1e-12 * span;
-        fixed[i] = (at_lo && sh.Jtr[i] > 0.0) || (at_hi && sh.Jtr[i] < 0.0);
-      }
-      double d[kMaxP];
-      int ok = lm_step(sh.JtJ, sh.Jtr, fixed, nP, lam, d) ? 1 : 0;
-      // per-coordinate fraction-to-boundary rule: a coordinate whose step would leave the box moves 99.5% of the
-      // way to that bound instead (the trial point stays strictly inside, as SciPy's TRF iterates do, so a wild
-      // step can never park tau on 0 where the model has no gradient); the other coordinates keep their step.
-      int tiny = 1, truncated = 0;          // tiny: every |step_i| < 1e-15 |p_i|
-      for (int i = 0; i < nP; ++i) {
-        double q = sh.p[i] + d[i];
-        if (q < sh.lo[i]) { q = sh.p[i] - 0.995 * (sh.p[i] - sh.lo[i]); truncated = 1; }
-        else if (q > sh.hi[i]) { q = sh.p[i] + 0.995 * (sh.hi[i] - sh.p[i]); truncated = 1; }
-        if (!(fabs(q - sh.p[i]) < 1e-15 * (fabs(sh.p[i]) + 1e-300))) tiny = 0;
-        sh.ptry[i] = q;
-      }
-      sh.trunc = truncated;
-      sh.flag = ok ? (tiny ? 2 : 1) : 0;
+#pragma unroll
+      for (int j = 0; j < N; ++j) R[k * N + j] = (j >= k) ? h.rrow[j] : 0.0;
+      qtf[k] = h.rrow[N];
     }
-    __syncthreads();
-    const int flag = sh.flag, trunc = sh.trunc;
-    __syncthreads();
-    if (flag == 0) { lam *= 10.0; if (lam > 1e20) { status = 3; break; } continue; }
-    if (flag == 2 && !trunc) { status = 2; break; }      // step below machine precision
-    evaluate<nP>(t, y, sig, L, sh.ptry, sh, sh.tJtJ, sh.tJtr, &sh.tcost);
-    const double c0 = sh.cost, c1 = sh.tcost;
-    const bool accept = (c1 <= c0) && (c1 == c1);
-    __syncthreads();
-    if (accept) {
-      if (threadIdx.x == 0) {
-        for (int i = 0; i < nP; ++i) { sh.p[i] = sh.ptry[i]; sh.Jtr[i] = sh.tJtr[i]; }
-        for (int i = 0; i < nP * nP; ++i) sh.JtJ[i] = sh.tJtJ[i];
-        sh.cost = c1;
+    if (h.vscale != 0.0) {
+      for (int i = i0; i < M; i += kFitThreads) {
+        const double vi = A[(size_t)k * Mp + i] * h.vscale;
+#pragma unroll
+        for (int j = 0; j <= N; ++j)
+          if (j > k) A[(size_t)j * Mp + i] -= h.tw[j] * vi;
       }
-      lam = fmax(lam * 0.3, 1e-12);
-      __syncthreads();
-      // converged: three consecutive negligible decreases taken with (almost) undamped Gauss-Newton steps.
-      // A tiny decrease under heavy damping only means the step was short (flat multi-exponential valleys).
-      small = (c0 - c1 <= ftol * c0 && !trunc) ? small + 1 : 0;    // a truncated step says nothing about convergence
-      if (small >= 3 && lam <= 1e-7) { status = 1; ++it; break; }
-    } else {
-      lam *= 4.0;
-      if (lam > 1e20) { status = 3; break; }
     }
+  }
+}
+
+template <int N>
+__global__ void __launch_bounds__(kFitThreads)
+ct_fit_trf_kernel(const double* __restrict__ T, const double* __restrict__ Y, const double* __restrict__ SIG, int L,
+                  const double* __restrict__ P0, const double* __restrict__ LO, const double* __restrict__ HI,
+                  int max_nfev, double ftol, double xtol, double gtol, double* __restrict__ POPT,
+                  double* __restrict__ ROUT, double* __restrict__ COST, int* __restrict__ STATUS, double* work,
+                  int in_smem) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  FitShared<N>& sh = *reinterpret_cast<FitShared<N>*>(smem_raw);
+  srtrf::Core<N>& c = sh.core;
+  const int r = blockIdx.x;
+  const int M = L + N, Mp = M;
+  Problem<N> pb;
+  pb.L = L;
+  pb.sig = SIG ? SIG + (size_t)r * L : nullptr;
+  double* A;
+  if (in_smem) {
+    double* base = reinterpret_cast<double*>(smem_raw + ((sizeof(FitShared<N>) + 15) / 16) * 16);
+    double* ts = base; double* ys = ts + L; double* ws = ys + L;
+    A = ws + L;
+    for (int k = threadIdx.x; k < L; k += kFitThreads) {
+      ts[k] = T[(size_t)r * L + k];
+      ys[k] = Y[(size_t)r * L + k];
+      ws[k] = pb.sig ? 1.0 / pb.sig[k] : 1.0;
+    }
+    pb.t = ts; pb.y = ys; pb.w = ws;
+  } else {
+    A = work + (size_t)r * Mp * (N + 1);
+    pb.t = T + (size_t)r * L; pb.y = Y + (size_t)r * L; pb.w = nullptr;
+  }
+  int parity = 0;
+  if (threadIdx.x == 0) {
+    bool feasible = true;
+    for (int i = 0; i < N; ++i) {
+      c.x[i] = P0[(size_t)r * N + i]; c.lb[i] = LO[(size_t)r * N + i]; c.ub[i] = HI[(size_t)r * N + i];
+      feasible = feasible && (c.x[i] >= c.lb[i]) && (c.x[i] <= c.ub[i]);
+    }
+    if (feasible) srtrf::make_strictly_feasible<N>(c.x, c.lb, c.ub, 1e-10);
+    sh.flag = feasible ? kFlagQR : kFlagStop;
+  }
+  __syncthreads();
+  if (sh.flag == kFlagStop) {                     // least_squares raises "`x0` is infeasible": a failed fit upstream
+    if (threadIdx.x == 0) {
+      for (int i = 0; i < N; ++i) POPT[(size_t)r * N + i] = c.x[i];
+      for (int i = 0; i < N * N; ++i) ROUT[(size_t)r * N * N + i] = 0.0;
+      COST[r] = INFINITY; STATUS[2 * r] = -3; STATUS[2 * r + 1] = 0;
+    }
+    return;
+  }
+  double g[N], cost;
+  eval_jac<N>(pb, c.x, A, Mp, sh, parity, g, cost);
+  if (!isfinite(cost)) {                          // "Residuals are not finite in the initial point"
+    if (threadIdx.x == 0) {
+      for (int i = 0; i < N; ++i) POPT[(size_t)r * N + i] = c.x[i];
+      for (int i = 0; i < N * N; ++i) ROUT[(size_t)r * N * N + i] = 0.0;
+      COST[r] = INFINITY; STATUS[2 * r] = -4; STATUS[2 * r + 1] = 1;
+    }
+    return;
   }
   if (threadIdx.x == 0) {
-    for (int i = 0; i < nP; ++i) POPT[(long long)r * nP + i] = sh.p[i];
-    for (int i = 0; i < nP * nP; ++i) JTJ[(long long)r * nP * nP + i] = sh.JtJ[i];
-    COST[r] = sh.cost;
-    STATUS[2 * r] = status; STATUS[2 * r + 1] = it;
+    for (int i = 0; i < N; ++i) c.g[i] = g[i];
+    c.cost = cost;
+    srtrf::begin<N>(c, L, max_nfev, ftol, xtol, gtol);
+    sh.flag = srtrf::outer_begin<N>(c) ? kFlagQR : kFlagStop;
   }
+  __syncthreads();
+  while (sh.flag == kFlagQR) {
+    // augmented, scaled Jacobian: data rows times d, then the n rows diag(sqrt(diag_h)); rhs rows below L are zero
+    for (int i = threadIdx.x; i < M; i += kFitThreads) {
+      if (i < L) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) A[(size_t)j * Mp + i] *= c.d[j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < N; ++j) A[(size_t)j * Mp + i] = (j == i - L) ? sqrt(c.diag_h[j]) : 0.0;
+        A[(size_t)N * Mp + i] = 0.0;
+      }
+    }
+    block_qr<N>(A, M, Mp, sh, parity, c.R, sh.qtf);
+    double cost_new = 0.0;
+    if (threadIdx.x == 0) {
+      srtrf::svd_setup<N>(c, sh.qtf);
+      sh.flag = srtrf::inner_propose<N>(c) ? kFlagTrial : (srtrf::outer_end<N>(c, 0.0) ? kFlagAccept : kFlagReject);
+    }
+    __syncthreads();
+    while (sh.flag == kFlagTrial) {
+      cost_new = eval_cost<N>(pb, c.x_new, sh, parity);       // barrier inside: every thread has read the flag
+      if (threadIdx.x == 0) {
+        const bool stop = srtrf::inner_judge<N>(c, cost_new, isfinite(cost_new));
+        if (!stop && srtrf::inner_propose<N>(c)) sh.flag = kFlagTrial;
+        else sh.flag = srtrf::outer_end<N>(c, cost_new) ? kFlagAccept : kFlagReject;
+      }
+      __syncthreads();
+    }
+    const bool accepted = (sh.flag == kFlagAccept);
+    __syncthreads();                                           // flag read by all before thread 0 rewrites it
+    if (accepted) {
+      eval_jac<N>(pb, c.x, A, Mp, sh, parity, g, cost);
+      if (threadIdx.x == 0)
+        for (int i = 0; i < N; ++i) c.g[i] = g[i];
+    }
+    if (threadIdx.x == 0) sh.flag = srtrf::outer_begin<N>(c) ? kFlagQR : kFlagStop;
+    __syncthreads();
+    if (sh.flag == kFlagQR && !accepted) {                     // cannot happen (a rejected outer step ends the solve)
+      if (threadIdx.x == 0) c.status = 0;
+      break;
+    }
+  }
+  // R factor of the unscaled Jacobian at the solution
+  eval_jac<N>(pb, c.x, A, Mp, sh, parity, g, cost);
+  block_qr<N>(A, L, Mp, sh, parity, c.R, sh.qtf);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < N; ++i) POPT[(size_t)r * N + i] = c.x[i];
+    for (int i = 0; i < N * N; ++i) ROUT[(size_t)r * N * N + i] = c.R[i];
+    COST[r] = c.cost;
+    STATUS[2 * r] = c.status; STATUS[2 * r + 1] = c.nfev;
+  }
+}
+
+template <int N>
+size_t fit_smem_bytes(long long L) {
+  return ((sizeof(FitShared<N>) + 15) / 16) * 16 + sizeof(double) * (size_t)(3 * L + (L + N) * (N + 1));
+}
+
+template <int N>
+int launch_fit(const double* d_t, const double* d_y, const double* d_sigma, int nR, long long L, const double* d_p0,
+               const double* d_lo, const double* d_hi, int max_nfev, double ftol, double xtol, double gtol,
+               double* d_popt, double* d_R, double* d_cost, int* d_status, void* d_work, size_t work_bytes,
+               cudaStream_t stream) {
+  size_t smem = fit_smem_bytes<N>(L);
+  int in_smem = smem <= kFitSmemLimit;
+  if (!in_smem) {
+    const size_t need = sizeof(double) * (size_t)nR * (L + N) * (N + 1);
+    if (!d_work || work_bytes < need) {
+      sr_set_error("sr_ct_fit_trf: curves of %lld points need a workspace of %zu bytes (got %zu)", L, need, work_bytes);
+      return SR_ERR_WORKSPACE;
+    }
+    smem = ((sizeof(FitShared<N>) + 15) / 16) * 16;
+  }
+  SR_CUDA(cudaFuncSetAttribute(ct_fit_trf_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFitSmemLimit));
+  ct_fit_trf_kernel<N><<<nR, kFitThreads, smem, stream>>>(d_t, d_y, d_sigma, (int)L, d_p0, d_lo, d_hi, max_nfev, ftol,
+                                                           xtol, gtol, d_popt, d_R, d_cost, d_status, (double*)d_work,
+                                                           in_smem);
+  SR_CUDA(cudaGetLastError());
+  return SR_OK;
 }
 
 }  // namespace
 
-extern "C" int sr_ct_fit_lm(const double* d_t, const double* d_y, const double* d_sigma, int nR, long long L, int nParams,
-                            const double* d_p0, const double* d_lo, const double* d_hi, int max_iter, double ftol,
-                            double* d_popt, double* d_JtJ, double* d_cost, int* d_status, void* stream) {
-  SR_REQUIRE(d_t && d_y && d_p0 && d_lo && d_hi && d_popt && d_JtJ && d_cost && d_status, "sr_ct_fit_lm: null pointer");
-  SR_REQUIRE(nR > 0 && L > 0 && L < (1LL << 31), "sr_ct_fit_lm: bad shape (nR=%d L=%lld)", nR, L);
-  SR_REQUIRE(nParams >= 2 && nParams <= kMaxP, "sr_ct_fit_lm: nParams %d outside [2, %d]", nParams, kMaxP);
-  SR_REQUIRE(max_iter > 0 && ftol >= 0, "sr_ct_fit_lm: bad solver settings");
-#define SR_FIT_CASE(NP)                                                                                     \
-  case NP:                                                                                                  \
-    ct_fit_lm_kernel<NP><<<nR, kFitThreads, 0, (cudaStream_t)stream>>>(d_t, d_y, d_sigma, (int)L, d_p0, d_lo, d_hi, \
-                                                                       max_iter, ftol, d_popt, d_JtJ, d_cost, d_status); \
-    break;
+extern "C" size_t sr_ct_fit_workspace_bytes(int nR, long long L, int nParams) {
+  if (nR <= 0 || L <= 0 || nParams < 2 || nParams > kMaxP) return 0;
+  const size_t smem = ((sizeof(FitShared<kMaxP>) + 15) / 16) * 16 + sizeof(double) * (size_t)(3 * L + (L + nParams) * (nParams + 1));
+  if (smem <= kFitSmemLimit - 1024) return 0;      // conservative: never reports 0 for a shape the launcher sends to the workspace
+  return sizeof(double) * (size_t)nR * (L + nParams) * (nParams + 1);
+}
+
+extern "C" int sr_ct_fit_trf(const double* d_t, const double* d_y, const double* d_sigma, int nR, long long L, int nParams,
+                             const double* d_p0, const double* d_lo, const double* d_hi, int max_nfev, double ftol,
+                             double xtol, double gtol, double* d_popt, double* d_R, double* d_cost, int* d_status,
+                             void* d_work, size_t work_bytes, void* stream) {
+  SR_REQUIRE(d_t && d_y && d_p0 && d_lo && d_hi && d_popt && d_R && d_cost && d_status, "sr_ct_fit_trf: null pointer");
+  SR_REQUIRE(nR > 0 && L > 0 && L < (1LL << 30), "sr_ct_fit_trf: bad shape (nR=%d L=%lld)", nR, L);
+  SR_REQUIRE(nParams >= 2 && nParams <= kMaxP, "sr_ct_fit_trf: nParams %d outside [2, %d]", nParams, kMaxP);
+  SR_REQUIRE(ftol >= 0 && xtol >= 0 && gtol >= 0, "sr_ct_fit_trf: negative tolerance");
+  if (max_nfev <= 0) max_nfev = 100 * nParams;     // SciPy's default for method='trf'
+#define SR_FIT_CASE(NP)                                                                                            \
+  case NP:                                                                                                         \
+    return launch_fit<NP>(d_t, d_y, d_sigma, nR, L, d_p0, d_lo, d_hi, max_nfev, ftol, xtol, gtol, d_popt, d_R, d_cost, \
+                          d_status, d_work, work_bytes, (cudaStream_t)stream);
   switch (nParams) {
     SR_FIT_CASE(2) SR_FIT_CASE(3) SR_FIT_CASE(4) SR_FIT_CASE(5) SR_FIT_CASE(6) SR_FIT_CASE(7) SR_FIT_CASE(8) SR_FIT_CASE(9)
   }
 #undef SR_FIT_CASE
-  SR_CUDA(cudaGetLastError());
-  return SR_OK;
+  return SR_ERR_ARG;
 }

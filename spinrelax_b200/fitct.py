@@ -1,5 +1,5 @@
 """Host mirror of fitting_Ct_functions.py: containers for C(t) = S2 + sum_i C_i exp(-t/tau_i) models, with the
-least-squares solve moved to the GPU (sr_ct_fit_lm, one CTA per residue) and batched over residues.
+least-squares solve moved to the GPU (sr_ct_fit_trf, one CTA per residue) and batched over residues.
 
 Kept from the reference, by name: autoCorrelations (add_model, add_target, import_target_array, export, ...),
 autoCorrelationModel (conduct_curve_fitting, optimised_curve_fitting, eval, calc_chiSq, set_nParams, report,
@@ -15,8 +15,9 @@ import numpy as np
 
 from . import _lib
 
-FTOL = 1e-14
-MAX_ITER = 2000
+# scipy.optimize.curve_fit's settings for the bounded ('trf') solver: SURVEY Appendix B
+FTOL = XTOL = GTOL = 1e-8
+MAX_NFEV = 0              # 0 = SciPy's default, 100 * nParams
 
 
 def curvefit_exponential(DeltaT, *params):
@@ -29,11 +30,12 @@ def curvefit_exponential(DeltaT, *params):
 
 
 # ---- GPU solve ----------------------------------------------------------------------------------------
-KERNEL_EVENTS = None      # set to a list to collect (start, end) CUDA event pairs around every sr_ct_fit_lm launch
+KERNEL_EVENTS = None      # set to a list to collect (start, end) CUDA event pairs around every sr_ct_fit_trf launch
 
 
 def _device_solve(t, y, sigma, p0, lo, hi):
-    """sr_ct_fit_lm on (nR, L) curves: returns popt (nR,nP), J^T J at the optimum (nR,nP,nP), cost (nR,), status (nR,2)."""
+    """sr_ct_fit_trf on (nR, L) curves: returns popt (nR,nP), the R factor of the Jacobian at the solution (nR,nP,nP),
+    cost (nR,) and status (nR,2) = (SciPy termination status, nfev)."""
     torch = _lib.require_cuda()
     lib = _lib.load()
     dev = torch.device("cuda")
@@ -44,50 +46,61 @@ def _device_solve(t, y, sigma, p0, lo, hi):
         f(np.broadcast_to(hi, (nR, nP)))
     sd = None if sigma is None else f(np.broadcast_to(sigma, (nR, L)))
     popt = torch.empty((nR, nP), dtype=torch.float64, device=dev)
-    JtJ = torch.empty((nR, nP, nP), dtype=torch.float64, device=dev)
+    R = torch.empty((nR, nP, nP), dtype=torch.float64, device=dev)
     cost = torch.empty(nR, dtype=torch.float64, device=dev)
     status = torch.empty((nR, 2), dtype=torch.int32, device=dev)
+    wbytes = int(lib.sr_ct_fit_workspace_bytes(nR, L, nP))
+    work = torch.empty(max(wbytes, 8) // 8, dtype=torch.float64, device=dev) if wbytes else None
     if KERNEL_EVENTS is not None:
         ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
         ev[0].record()
-    _lib.check(lib.sr_ct_fit_lm(td.data_ptr(), yd.data_ptr(), 0 if sd is None else sd.data_ptr(), nR, L, nP,
-                                p0d.data_ptr(), lod.data_ptr(), hid.data_ptr(), MAX_ITER, FTOL, popt.data_ptr(),
-                                JtJ.data_ptr(), cost.data_ptr(), status.data_ptr(), _lib.current_stream_ptr()),
-               "sr_ct_fit_lm")
+    _lib.check(lib.sr_ct_fit_trf(td.data_ptr(), yd.data_ptr(), 0 if sd is None else sd.data_ptr(), nR, L, nP,
+                                 p0d.data_ptr(), lod.data_ptr(), hid.data_ptr(), MAX_NFEV, FTOL, XTOL, GTOL,
+                                 popt.data_ptr(), R.data_ptr(), cost.data_ptr(), status.data_ptr(),
+                                 0 if work is None else work.data_ptr(), wbytes, _lib.current_stream_ptr()),
+               "sr_ct_fit_trf")
     if KERNEL_EVENTS is not None:
         ev[1].record()
         KERNEL_EVENTS.append(ev)
-    return popt.cpu().numpy(), JtJ.cpu().numpy(), cost.cpu().numpy(), status.cpu().numpy()
+    return popt.cpu().numpy(), R.cpu().numpy(), cost.cpu().numpy(), status.cpu().numpy()
 
 
-def pcov_from_normal_matrix(JtJ, cost, L):
-    """Covariance the way scipy.optimize.curve_fit forms it (SVD of J, singular values <= eps*max(M,n)*s0 dropped,
-    pcov = V S^-2 V^T * 2 cost/(M-n)), from the eigen-decomposition of J^T J, batched over the residues."""
-    nP = JtJ.shape[-1]
-    bad = ~np.all(np.isfinite(JtJ), axis=(1, 2))       # diverged fits: keep LAPACK away from NaNs, mark them below
+def pcov_from_R(R, cost, L):
+    """Covariance as scipy.optimize.curve_fit forms it from svd(J) (singular values <= eps*max(M,n)*s0 dropped,
+    pcov = V S^-2 V^T * 2 cost/(M-n)), batched over the residues.  R is the triangular factor of J = Q R: same
+    singular values and right singular vectors as J, without squaring the condition number."""
+    nP = R.shape[-1]
+    bad = ~np.all(np.isfinite(R), axis=(1, 2))         # keep LAPACK away from NaNs; those rows are marked below
     if np.any(bad):
-        JtJ = JtJ.copy()
-        JtJ[bad] = 0.0
-    w, V = np.linalg.eigh(JtJ)
-    sv = np.sqrt(np.clip(w, 0.0, None))
-    keep = sv > (np.finfo(float).eps * max(L, nP)) * sv.max(axis=1, keepdims=True)
+        R = R.copy()
+        R[bad] = 0.0
+    _, sv, VT = np.linalg.svd(R)
+    keep = sv > (np.finfo(float).eps * max(L, nP)) * sv[:, :1]
     with np.errstate(divide="ignore", invalid="ignore"):
         inv = np.where(keep, 1.0 / (sv * sv), 0.0)
-    pcov = np.einsum("rik,rk,rjk->rij", V, inv, V)
+    pcov = np.einsum("rki,rk,rkj->rij", VT, inv, VT)
     if L > nP:
         pcov *= (2.0 * cost / (L - nP))[:, None, None]
     else:
         pcov[:] = np.inf
-    pcov[bad] = np.nan
+    pcov[bad] = np.inf                                  # curve_fit: indeterminate covariance is filled with inf
     return pcov
+
+
+def fit_succeeded(status):
+    """curve_fit raises (and the reference's bare `except` turns that into chi = inf, bQuality[0] = False,
+    fitting_Ct_functions.py:325-328) when least_squares does not report success: termination status 0 = max_nfev
+    reached, or the ValueErrors for an infeasible p0 / non-finite residuals (negative codes here)."""
+    return np.asarray(status)[..., 0] > 0
 
 
 def gpu_curve_fit(t, y, sigma, p0, lo, hi):
     """Batched bounded least squares.  t, y, sigma: (nR, L) (sigma may be None); p0, lo, hi: (nR, nP).
-    Returns popt (nR,nP), pcov (nR,nP,nP) formed like scipy.optimize.curve_fit, cost (nR,), status (nR,2)."""
+    Returns popt (nR,nP), pcov (nR,nP,nP) formed like scipy.optimize.curve_fit, cost (nR,), status (nR,2);
+    rows with fit_succeeded(status) False are the ones curve_fit would have raised on."""
     t, y, p0 = np.atleast_2d(t), np.atleast_2d(y), np.atleast_2d(p0)
-    popt, JtJ, cost, status = _device_solve(t, y, sigma, p0, lo, hi)
-    return popt, pcov_from_normal_matrix(JtJ, cost, y.shape[1]), cost, status
+    popt, R, cost, status = _device_solve(t, y, sigma, p0, lo, hi)
+    return popt, pcov_from_R(R, cost, y.shape[1]), cost, status
 
 
 # ---- containers ------------------------------------------------------------------------------------
@@ -275,7 +288,7 @@ class autoCorrelationModel:
         p0 = np.array(self.get_params_as_list(), dtype=float)
         popt, pcov, cost, status = gpu_curve_fit(DeltaT, Decay, dDecay, p0[None, :], np.full_like(p0, lo)[None, :],
                                                  np.array(hi, dtype=float)[None, :])
-        if not np.all(np.isfinite(popt[0])) or not np.isfinite(cost[0]):
+        if not fit_succeeded(status)[0]:
             print("= = = WARNING, curve fitting of %s with %i params failed!" % (self.name, self.nParams), file=fp)
             return np.inf, [False, True, True]
         return self._absorb_fit(popt[0], pcov[0], DeltaT, Decay, dDecay, fp)
@@ -434,7 +447,7 @@ class autoCorrelations:
             hi = np.concatenate((np.ones((a.size, nc)), np.repeat((T[a, -1] * 10)[:, None], nc, axis=1)) +
                                 ((np.ones((a.size, 1)),) if fast else ()), axis=1)
             popt, pcov, cost, status = gpu_curve_fit(T[a], Y[a], None if SG is None else SG[a], p0, np.zeros_like(p0), hi)
-            finite = np.all(np.isfinite(popt), axis=1)
+            finite = fit_succeeded(status)                            # False where curve_fit raises upstream (:325-328)
             with np.errstate(invalid="ignore"):
                 dParam = np.sqrt(np.diagonal(pcov, axis1=1, axis2=2))
                 # quality flags as conduct_curve_fitting raises them, i.e. on the initial-guess state (:329-337, quirk G6)
@@ -478,6 +491,8 @@ class autoCorrelations:
                         lines.append("= = = WARNING, curve fitting of %s with %i params indicates overfitting." % (names[i], nParams))
                     if not q_sum[j]:
                         lines.append("= = = WARNING, curve fitting of %s with %i params returns sum>1." % (names[i], nParams))
+                else:
+                    lines.append("= = = WARNING, curve fitting of %s with %i params failed!" % (names[i], nParams))
                 lines.append("    ...%s: fit with %i params yield chiSq of %g" % (names[i], nParams, chi[j]))
             # selection ladder (optimised_curve_fitting :288-304)
             was_first = first[a]
@@ -553,7 +568,8 @@ class autoCorrelations:
             for j, i in enumerate(active):
                 k = keys[i]
                 m = work[k]
-                if not np.all(np.isfinite(popt[j])):
+                if not fit_succeeded(status)[j]:
+                    print("= = = WARNING, curve fitting of %s with %i params failed!" % (m.name, nParams), file=fp)
                     chiSq, bQ = np.inf, [False, True, True]
                 else:
                     chiSq, bQ = m._absorb_fit(popt[j], pcov[j], T[i], Y[i], None if SG is None else SG[i], fp)

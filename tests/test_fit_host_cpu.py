@@ -22,7 +22,7 @@ def test_fit_cli_reproduces_reference_file(golden, tmp_path, monkeypatch, tag, e
 
 
 def test_device_solve_marshals_arguments_as_the_header_declares(monkeypatch):
-    """`fitct._device_solve` against a stand-in library whose `sr_ct_fit_lm` takes its parameters in the order parsed
+    """`fitct._device_solve` against a stand-in library whose `sr_ct_fit_trf` takes its parameters in the order parsed
     from include/spinrelax_b200.h, reads the buffers through the raw pointers it is handed and writes results back
     the same way: catches a wrong argument order / dtype / shape in the ctypes call without a GPU."""
     import ctypes
@@ -34,7 +34,7 @@ def test_device_solve_marshals_arguments_as_the_header_declares(monkeypatch):
     from spinrelax_b200 import _lib, fitct
 
     hdr = open(os.path.join(ROOT, "include", "spinrelax_b200.h")).read()
-    decl = re.search(r"int\s+sr_ct_fit_lm\s*\(([^;]*)\)\s*;", hdr, re.S).group(1)
+    decl = re.search(r"int\s+sr_ct_fit_trf\s*\(([^;]*)\)\s*;", hdr, re.S).group(1)
     names = [p.strip().split()[-1].lstrip("*") for p in decl.replace("\n", " ").split(",")]
     seen = {}
 
@@ -44,16 +44,20 @@ def test_device_solve_marshals_arguments_as_the_header_declares(monkeypatch):
         return np.frombuffer((ctype * n).from_address(int(ptr)), dtype=dtype).reshape(shape)
 
     class FakeLib:
+        def sr_ct_fit_workspace_bytes(nR, L, nP):
+            return 0
+
         @staticmethod
-        def sr_ct_fit_lm(*args):
+        def sr_ct_fit_trf(*args):
             a = dict(zip(names, args))
             nR, L, nP = int(a["nR"]), int(a["L"]), int(a["nParams"])
-            seen.update(nR=nR, L=L, nP=nP, max_iter=int(a["max_iter"]), ftol=float(a["ftol"]),
+            seen.update(nR=nR, L=L, nP=nP, max_nfev=int(a["max_nfev"]), ftol=float(a["ftol"]), xtol=float(a["xtol"]),
+                        gtol=float(a["gtol"]), work=a["d_work"], work_bytes=int(a["work_bytes"]),
                         t=view(a["d_t"], (nR, L)).copy(), y=view(a["d_y"], (nR, L)).copy(),
                         sigma=view(a["d_sigma"], (nR, L)).copy(), p0=view(a["d_p0"], (nR, nP)).copy(),
                         lo=view(a["d_lo"], (nR, nP)).copy(), hi=view(a["d_hi"], (nR, nP)).copy())
             view(a["d_popt"], (nR, nP))[:] = seen["p0"] + 1.0
-            view(a["d_JtJ"], (nR, nP, nP))[:] = np.eye(nP)[None] * np.arange(1, nR + 1)[:, None, None]
+            view(a["d_R"], (nR, nP, nP))[:] = np.eye(nP)[None] * np.arange(1, nR + 1)[:, None, None]
             view(a["d_cost"], (nR,))[:] = np.arange(nR) + 0.5
             view(a["d_status"], (nR, 2), ctypes.c_int32, np.int32)[:] = [[1, 7]] * nR
             return 0
@@ -73,14 +77,15 @@ def test_device_solve_marshals_arguments_as_the_header_declares(monkeypatch):
     nR, L, nP = 4, 11, 5
     t, y, sg = np.arange(1.0, L + 1), rng.random((nR, L)), rng.random((nR, L)) + 0.1
     p0, hi = rng.random((nR, nP)), np.full((nR, nP), 9.0)
-    popt, JtJ, cost, status = fitct._device_solve(np.atleast_2d(t), y, sg, p0, np.zeros_like(p0), hi)
+    popt, Rf, cost, status = fitct._device_solve(np.atleast_2d(t), y, sg, p0, np.zeros_like(p0), hi)
     assert (seen["nR"], seen["L"], seen["nP"]) == (nR, L, nP)
-    assert seen["max_iter"] == fitct.MAX_ITER and seen["ftol"] == fitct.FTOL
+    assert seen["max_nfev"] == fitct.MAX_NFEV == 0 and (seen["ftol"], seen["xtol"], seen["gtol"]) == (1e-8, 1e-8, 1e-8)
+    assert seen["work_bytes"] == 0 and not seen["work"]
     assert np.array_equal(seen["t"], np.broadcast_to(t, (nR, L))) and np.array_equal(seen["y"], y)
     assert np.array_equal(seen["sigma"], sg) and np.array_equal(seen["p0"], p0)
     assert np.array_equal(seen["lo"], np.zeros((nR, nP))) and np.array_equal(seen["hi"], hi)
     assert np.array_equal(popt, p0 + 1.0) and np.array_equal(cost, np.arange(nR) + 0.5)
-    assert np.array_equal(JtJ[2], 3.0 * np.eye(nP)) and np.array_equal(status, [[1, 7]] * nR)
-    # and through the public wrapper: covariance from those J^T J / cost values
+    assert np.array_equal(Rf[2], 3.0 * np.eye(nP)) and np.array_equal(status, [[1, 7]] * nR)
+    # and through the public wrapper: covariance from those R factors (J^T J = R^T R = 4 I for row 1) and costs
     popt2, pcov, cost2, _ = fitct.gpu_curve_fit(t, y, sg, p0, np.zeros_like(p0), hi)
-    assert np.allclose(pcov[1], np.eye(nP) / 2.0 * (2.0 * 1.5 / (L - nP)))
+    assert np.allclose(pcov[1], np.eye(nP) / 4.0 * (2.0 * 1.5 / (L - nP)))

@@ -121,7 +121,8 @@ def _rates(fitct, sd, models_ac):
 
 
 def test_fit_single_rungs_vs_golden(golden):
-    """Same p0/bounds as the reference: chi^2 and the fitted curve must agree; parameters where well determined."""
+    """Same p0/bounds as the reference (real fitting_Ct_functions.py on SciPy, tests/golden/fit.npz): chi^2, the
+    quality flags and the parameters of every well-posed rung."""
     from spinrelax_b200 import fitct
     g = golden("fit.npz")
     t, Ct, dCt = g["t"], g["Ct"], g["dCt"]
@@ -132,18 +133,19 @@ def test_fit_single_rungs_vs_golden(golden):
             m = fitct.autoCorrelationModel(name=i)
             m.set_nParams(npar)
             chi, qual = m.conduct_curve_fitting(t, Ct[i], dCt[i], bReInitialise=True, fp=io.StringIO())
+            assert np.isfinite(chi) == np.isfinite(r[1]), (i, npar)        # fails exactly where curve_fit raised upstream
+            assert [float(b) for b in qual] == list(r[2:5]), (i, npar)
             if not np.isfinite(r[1]):
                 continue
-            # chi (mean r^2/sigma, :276) is not the least-squares cost, and SciPy stops at ftol=1e-8: agree to 1e-4
-            assert rel_err(chi, r[1]) < 1e-4, (i, npar, chi, r[1])
+            assert rel_err(chi, r[1]) < 1e-6, (i, npar, chi, r[1])
             if npar <= 3:
                 nc = npar // 2
-                assert rel_err(m.C, r[6:6 + nc]) < 1e-4 and rel_err(m.tau, r[9:9 + nc]) < 1e-4
-                assert [float(b) for b in qual] == list(r[2:5])
+                assert rel_err(m.C, r[6:6 + nc]) < 1e-6 and rel_err(m.tau, r[9:9 + nc]) < 1e-6
 
 
 def test_fit_ladder_rates_vs_reference(golden):
-    """Full ladder on the GPU, then isotropic J -> R1/R2/NOE: rates within 1e-4 of the reference chain."""
+    """Full ladder on the GPU, then isotropic J -> R1/R2/NOE: the rung the reference chose for every residue, and rates
+    within 1e-4 of the reference chain."""
     from spinrelax_b200 import fitct, specdens as sd
     g = golden("fit.npz")
     t, Ct, dCt = g["t"], g["Ct"], g["dCt"]
@@ -156,13 +158,11 @@ def test_fit_ladder_rates_vs_reference(golden):
         nc = int(row[0]) // 2
         ref.add_model(str(i), name=i, listC=list(row[3:3 + nc]), listTau=list(row[7:7 + nc]), S2=row[2],
                       bS2Fast=(int(row[0]) % 2 == 1))
-    same = [ac.model[str(i)].nParams == int(g["ladder"][i][0]) for i in range(nres)]
-    assert sum(same) >= nres - 1, same          # model selection agrees (one threshold case tolerated)
+        assert ac.model[str(i)].nParams == int(row[0]), i
     a, b = _rates(fitct, sd, ac), _rates(fitct, sd, ref)
     for i in range(nres):
-        if same[i]:
-            assert rel_err(a[:, :, i], b[:, :, i]) < RTOL_RATE, i
-            assert rel_err(chis[i], g["ladder"][i][1]) < 1e-4
+        assert rel_err(a[:, :, i], b[:, :, i]) < RTOL_RATE, i
+        assert rel_err(chis[i], g["ladder"][i][1]) < 1e-6
     # one model at a time through the reference-shaped API gives the same answer as the batched ladder
     m = fitct.autoCorrelationModel(name=0)
     chi = m.optimised_curve_fitting(t, Ct[0], dCt[0], fp=io.StringIO())
@@ -170,7 +170,7 @@ def test_fit_ladder_rates_vs_reference(golden):
 
 
 def test_fit_against_scipy_oracle_random():
-    """Fresh curves, oracle = SciPy TRF (the reference's solver) run here: fitted curve and rates agree."""
+    """Fresh curves, oracle = SciPy TRF (the reference's solver) run here: same rung, fitted curve and rates agree."""
     from spinrelax_b200 import fitct, specdens as sd
     rng = np.random.default_rng(42)
     t = (np.arange(400) + 1.0) * 5.0
@@ -185,18 +185,80 @@ def test_fit_against_scipy_oracle_random():
     ac.import_target_array([str(i) for i in range(n)], [t] * n, np.array(Y), np.array(SG))
     ac.fit_all_residues(fp=io.StringIO())
     ref = fitct.autoCorrelations()
-    agree = 0
     for i in range(n):
         best = fit_oracle.fit_ladder(t, Y[i], SG[i])
         ref.add_model(str(i), name=i, listC=list(best["C"]), listTau=list(best["tau"]), S2=best["S2"],
                       bS2Fast=(best["n_params"] % 2 == 1))
-        agree += int(best["n_params"] == ac.model[str(i)].nParams)
-    assert agree >= n - 2
+        assert best["n_params"] == ac.model[str(i)].nParams, i
     a, b = _rates(fitct, sd, ac), _rates(fitct, sd, ref)
-    ok = [ac.model[str(i)].nParams == ref.model[str(i)].nParams for i in range(n)]
-    assert rel_err(a[:, :2, ok], b[:, :2, ok]) < RTOL_RATE                       # R1, R2
+    assert rel_err(a[:, :2], b[:, :2]) < RTOL_RATE                               # R1, R2
     # NOE crosses zero at 800 MHz for the poorly fitting 2-parameter models: 1e-4 of its O(1) scale
-    assert np.allclose(a[:, 2, ok], b[:, 2, ok], rtol=RTOL_RATE, atol=2e-5)
+    assert np.allclose(a[:, 2], b[:, 2], rtol=RTOL_RATE, atol=2e-5)
+
+
+def test_config5_all_1000_residues_vs_scipy_oracle():
+    """BASELINE config 5: the 1000 synthetic residues of the fit benchmark, whole 2-3-5-7-9 ladder on the GPU against
+    the oracle's ladder on SciPy (about 35 s of CPU).  Gates: the same rung on >= 99 % of the residues (every
+    disagreement is printed with both chi^2 so the margin to the 0.5 threshold can be read), and on every agreeing
+    residue chi^2 <= 1e-6, parameters <= 1e-4 and R1/R2/NOE at two fields <= 1e-4 of the reference chain.  Also:
+    every solve that hit SciPy's evaluation cap (curve_fit raises -> the reference's `failed!` path) is reported as
+    failed, and fewer than 0.5 % of the solves the *selected* ladders depend on end that way."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+    from bench_secondary import synth_curves
+    from spinrelax_b200 import fitct, specdens as sd
+    n = 1000
+    t, Y, SG = synth_curves(n, 500, 77)
+    ac = fitct.autoCorrelations()
+    ac.import_target_array([str(i) for i in range(n)], [t] * n, Y, SG)
+    log = io.StringIO()
+    chis = ac.fit_all_residues(fp=log)
+    ref = fitct.autoCorrelations()
+    refs, bad = [], []
+    for i in range(n):
+        best = fit_oracle.fit_ladder(t, Y[i], SG[i])
+        refs.append(best)
+        ref.add_model(str(i), name=i, listC=list(best["C"]), listTau=list(best["tau"]), S2=best["S2"],
+                      bS2Fast=(best["n_params"] % 2 == 1))
+        if best["n_params"] != ac.model[str(i)].nParams:
+            bad.append((i, ac.model[str(i)].nParams, best["n_params"], float(chis[i]), float(best["chi"])))
+    for row in bad:
+        print("selection differs: residue %d ours nParams=%d chi=%g, oracle nParams=%d chi=%g" % (row[0], row[1], row[3], row[2], row[4]))
+    assert len(bad) <= n // 100, bad
+    same = np.array([ac.model[str(i)].nParams == refs[i]["n_params"] for i in range(n)])
+    a, b = _rates(fitct, sd, ac), _rates(fitct, sd, ref)
+    worst = 0.0
+    for i in np.nonzero(same)[0]:
+        m, r = ac.model[str(i)], refs[i]
+        assert rel_err(chis[i], r["chi"]) < 1e-6, i
+        assert rel_err(m.tau, r["tau"]) < 1e-4 and np.max(np.abs(m.C - r["C"])) < 1e-4 and abs(m.S2 - r["S2"]) < 1e-4, i
+        assert rel_err(a[:, :2, i], b[:, :2, i]) < RTOL_RATE, i
+        assert np.allclose(a[:, 2, i], b[:, 2, i], rtol=RTOL_RATE, atol=2e-5), i
+        worst = max(worst, rel_err(a[:, :2, i], b[:, :2, i]))
+    print("config 5: %d/%d rungs agree, worst R1/R2 deviation %.3g" % (int(same.sum()), n, worst))
+    # the cap: count the reference's own `failed!` lines among all solves of the ladders (about 3000 here)
+    n_solves = log.getvalue().count("yield chiSq")
+    n_failed = log.getvalue().count("failed!")
+    assert n_failed <= 0.02 * n_solves, (n_failed, n_solves)
+
+
+def test_fit_long_curves_use_the_global_workspace():
+    """Curves too long for shared memory (L = 6000 > ~1900 points) take the workspace path of the kernel: same result
+    as the oracle on a subsampled-equivalent problem solved by SciPy directly."""
+    from spinrelax_b200 import fitct
+    rng = np.random.default_rng(5)
+    L, n = 6000, 3
+    t = (np.arange(L) + 1.0) * 2.0
+    Y = np.array([0.8 + 0.15 * np.exp(-t / tau) + rng.standard_normal(L) * 0.002 for tau in (150.0, 700.0, 2500.0)])
+    SG = np.full((n, L), 0.004)
+    ac = fitct.autoCorrelations()
+    ac.import_target_array([str(i) for i in range(n)], [t] * n, Y, SG)
+    chis = ac.fit_all_residues(fp=io.StringIO())
+    for i in range(n):
+        best = fit_oracle.fit_ladder(t, Y[i], SG[i])
+        m = ac.model[str(i)]
+        assert m.nParams == best["n_params"], i
+        assert rel_err(chis[i], best["chi"]) < 1e-6 and rel_err(m.tau, best["tau"]) < 1e-5
 
 
 def test_cli_relax_and_fit_files(golden, tmp_path):
