@@ -1,0 +1,9 @@
+"""Drop-in for SpinRelax's `npufunc` module: the same names, implemented by spinrelax_b200.npufunc (device stages on the GPU)."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from spinrelax_b200 import npufunc as _impl  # noqa: E402
+from spinrelax_b200.npufunc import *  # noqa: E402,F401,F403
+
+globals().update({k: v for k, v in vars(_impl).items() if not k.startswith('__')})

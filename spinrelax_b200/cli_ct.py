@@ -61,11 +61,20 @@ def build_parser():
     p.add_argument('--Hsel', '--selection', type=str, dest='Hseltxt', default='name H', help='Accepted, unused.')
     p.add_argument('--Xsel', type=str, dest='Xseltxt', default='name N and not resname PRO', help='Accepted, unused.')
     p.add_argument('--fitsel', type=str, dest='fittxt', default='custom occupancy', help='Accepted, unused.')
+    p.add_argument('--help_sel', action='store_true', help='Display help for selection texts and exit.')
     return p
 
 
+def print_selection_help():
+    """calculate-Ct-from-traj.py:17-19, plus what replaces the selection texts on this path."""
+    print("Notes: This python program uses MDTraj as its underlying engine to analyse trajectories and select atoms.")
+    print("It uses selection syntax such as 'chain A and resname GLY and name HA1 HA2', in a manner similar to GROMACS and VMD.")
+    print("On this path coordinates enter as arrays: give the atom index lists as `indexH`, `indexX` and `fit` in the input .npz;"
+          " --Hsel / --Xsel / --fitsel are accepted and ignored.")
+
+
 def _load_reference(fn):
-    ref = np.load(fn, allow_pickle=True)
+    ref = np.load(fn, allow_pickle=False)       # our own input format: plain arrays only, never unpickle user files
     if not isinstance(ref, np.ndarray):
         ref = ref['xyz']
     ref = np.asarray(ref, dtype=np.float32)
@@ -95,7 +104,7 @@ def _load(fn, ref_fn=None):
     if fn.endswith('.npy'):
         return np.load(fn), None, None, None
     if fn.endswith('.npz'):
-        z = np.load(fn, allow_pickle=True)
+        z = np.load(fn, allow_pickle=False)     # `names` must be a unicode or integer array, not an object array
         names = list(z['names']) if 'names' in z else None
         dt = float(z['dt']) if 'dt' in z else None
         if 'xyz' in z:
@@ -126,6 +135,10 @@ def _spherical_by_residue(frames, q_rot=None):
 
 
 def main(argv=None):
+    argv = sys.argv[1:] if argv is None else list(argv)
+    if '--help_sel' in argv:                           # upstream -s and -f are required, but --help_sel exits first (:350-352)
+        print_selection_help()
+        sys.exit(0)
     args = build_parser().parse_args(argv)
     time_start = time.time()
     tau_memory = args.tau

@@ -379,6 +379,48 @@ def build_parser():
     return p
 
 
+def rotmatrix_to_quaternion(time_axis, matrix, bInvert=False):
+    """calculate-dq-distribution.py:389-408 for `gmx rotmat` input: every row of nine matrix elements -> unit
+    quaternion (transforms3d `mat2quat`: principal eigenvector of the symmetric 4x4 K matrix, w made non-negative),
+    inverted when bInvert (`qinverse` = conjugate / |q|^2).  Returns the (5, n) time + w x y z table the PLUMED
+    reader returns.  Input conversion on the host (one batched eigh); transforms3d is a third-party dependency absent
+    from this image, restated from its published algorithm."""
+    n = len(time_axis)
+    if n != len(matrix):
+        print("= = = ERROR in rotmatrix_to_quaternion: lengths are not the same!", file=sys.stderr)
+        return None
+    M = np.asarray(matrix, dtype=float).reshape(n, 9)
+    Qxx, Qyx, Qzx, Qxy, Qyy, Qzy, Qxz, Qyz, Qzz = (M[:, i] for i in range(9))     # mat2quat reads M.flat in this order
+    K = np.zeros((n, 4, 4))
+    K[:, 0, 0] = Qxx - Qyy - Qzz
+    K[:, 1, 0], K[:, 1, 1] = Qyx + Qxy, Qyy - Qxx - Qzz
+    K[:, 2, 0], K[:, 2, 1], K[:, 2, 2] = Qzx + Qxz, Qzy + Qyz, Qzz - Qxx - Qyy
+    K[:, 3, 0], K[:, 3, 1], K[:, 3, 2], K[:, 3, 3] = Qyz - Qzy, Qzx - Qxz, Qxy - Qyx, Qxx + Qyy + Qzz
+    K /= 3.0
+    vals, vecs = np.linalg.eigh(K)                     # lower triangle, as numpy's default UPLO='L'
+    top = np.argmax(vals, axis=1)
+    q = np.take_along_axis(vecs, top[:, None, None], axis=2)[:, [3, 0, 1, 2], 0]
+    q = np.ascontiguousarray(np.where(q[:, :1] < 0, -q, q))
+    if bInvert:
+        # |q|^2 as np.dot(q, q) rounds it for one contiguous quaternion (the batched matmul takes the same BLAS path;
+        # a plain sum over the last axis differs in the last bit for a quarter of the frames)
+        n2 = np.matmul(q[:, None, :], q[:, :, None])[:, 0, :]
+        q = q * np.array([1.0, -1.0, -1.0, -1.0]) / n2
+    out = np.zeros((5, n))
+    out[0] = time_axis
+    out[1:5] = q.T
+    return out
+
+
+def read_quaternion_input(fn):
+    """Input dispatch of calculate-dq-distribution.py:487-500: `.xvg` = GROMACS `gmx rotmat` rotation matrices
+    (converted with bInvert=True), anything else = PLUMED print file.  Returns (fields, data (5+, n))."""
+    if fn.endswith('.xvg'):
+        x, y = io_formats.load_xys(fn)
+        return ["time", "w", "x", "y", "z"], rotmatrix_to_quaternion(x, y, bInvert=True)
+    return io_formats.read_from_plumedprint(fn)
+
+
 def main(argv=None):
     time_start = time.time()
     args = build_parser().parse_args(argv)
@@ -386,10 +428,10 @@ def main(argv=None):
         print("= = ERROR in input: histogram output type must be either dx, or dat, or none.")
         sys.exit()
     infn = [args.infn] if isinstance(args.infn, str) else list(args.infn)
-    fields, data = io_formats.read_from_plumedprint(infn[0])
+    fields, data = read_quaternion_input(infn[0])
     replicas = [data]
     for fn in infn[1:]:
-        _, d = io_formats.read_from_plumedprint(fn)
+        _, d = read_quaternion_input(fn)
         if d.shape != data.shape:
             print("= = ERROR: replica trajectories must have identical lengths (%s vs %s)." % (d.shape, data.shape),
                   file=sys.stderr)

@@ -49,6 +49,19 @@ def read_from_plumedprint(fname):
     return names, data
 
 
+def load_xys(fn):
+    """general_scripts.load_xys (:58-67): xmgrace/xvg text -> x (n,), y (n, ncol-1); '#', '@', '&' lines skipped."""
+    x, y = [], []
+    with open(fn) as fp:
+        for l in fp:
+            if l == "" or l[0] in "#@&":
+                continue
+            v = [float(i) for i in l.split()]
+            x.append(v[0])
+            y.append(v[1:])
+    return np.array(x), np.array(y)
+
+
 def print_xylist(fn, x, ylist, bCols=False, header=""):
     """x (nvals), ylist (nplots, nvals); bCols puts all plots on one line (`%g` columns)."""
     ylist = np.array(ylist)

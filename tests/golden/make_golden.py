@@ -635,6 +635,46 @@ def golden_relax_opt():
     save("relax_opt.npz", csa_true=csa_true, **{"expt_" + k: np.array(v) for k, v in expt.items()}, **res)
 
 
+def golden_dq_xvg():
+    """`gmx rotmat` input of calculate-dq-distribution.py (:389-408, 487-492): the real load_xys +
+    rotmatrix_to_quaternion(bInvert=True) on an .xvg text of rotation matrices, and the real CLI run on that file."""
+    import subprocess
+    import tempfile
+    refdq = ref_loader.script("calculate-dq-distribution.py")
+    gs = ref_loader.module("general_scripts")
+    qq = synth.quaternion_walk(4000, seed=synth.BASE_SEED + 41, sigma=(0.004, 0.006, 0.012), dtype=np.float64)
+    w, x, y, z = qq.T
+    # rotation matrix of the *inverse* rotation is what gmx rotmat reports relative to the reference; any proper
+    # rotation matrices will do for the parser and the converter
+    R = np.stack([1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w),
+                  2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w),
+                  2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)], axis=1)
+    lines = ["# This file was created by a test generator in the format of gmx rotmat", "@    title \"Fit matrix\"",
+             "@    xaxis  label \"Time (ps)\"", "@TYPE xy", "@ s0 legend \"xx\""]
+    for i in range(len(R)):
+        lines.append("%12.3f" % (i * 10.0) + "".join(" %10.6f" % v for v in R[i]))
+    lines.append("&")
+    text = "\n".join(lines) + "\n"
+    with tempfile.TemporaryDirectory() as td:
+        fn = os.path.join(td, "rotmat.xvg")
+        with open(fn, "w") as fp:
+            fp.write(text)
+        t, m = gs.load_xys(fn)
+        with quiet():
+            data = refdq.rotmatrix_to_quaternion(t, m, bInvert=True)
+        env = dict(os.environ, PYTHONPATH=os.pathsep.join([ref_loader.STUBS, ref_loader.REF_BUILD, ref_loader.REFERENCE]))
+        cmd = [sys.executable, os.path.join(ref_loader.REFERENCE, "calculate-dq-distribution.py"), "--iso", "--aniso",
+               "-f", fn, "-o", os.path.join(td, "rotdif"), "--mindt", "200", "--skip", "200", "--maxdt", "10000",
+               "--num_chunk", "4"]
+        subprocess.run(cmd, env=env, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, cwd=td)
+        files = {}
+        for suf in ("-iso.dat", "-aniso2.dat", "-aniso_q.dat"):
+            with open(os.path.join(td, "rotdif" + suf)) as fp:
+                files[suf] = fp.read()
+    save("dq_xvg.npz", xvg=np.array(text), data=data, iso=np.array(files["-iso.dat"]), aniso2=np.array(files["-aniso2.dat"]),
+         aniso_q=np.array(files["-aniso_q.dat"]))
+
+
 def main():
     if not ref_loader.available():
         sys.exit("reference tree not found at %s" % ref_loader.REFERENCE)
@@ -654,6 +694,7 @@ def main():
     golden_sd_host()
     golden_dq(refdq)
     golden_dq_multi(refdq)
+    golden_dq_xvg()
     golden_fit()
     golden_relax()
     golden_relax_cli()
