@@ -73,10 +73,6 @@ int sr_ct_lag_sums(const void* d_packed, long long pitch, int nC, long long nF, 
 int sr_ct_lag_sums_chunks(const void* d_packed, long long pitch, int nC, int c0, int nCsub, long long nF, int nR,
                           long long L, double* d_S, void* stream);
 
-/* Same kernel with an explicit tile configuration (tuning / profiling only; 0 .. 12, see csrc/ct.cu). */
-int sr_ct_lag_sums_variant(const void* d_packed, long long pitch, int nC, long long nF, int nR, long long L,
-                           double* d_S, int variant, void* stream);
-
 /* per-chunk mean -> mean and std/(sqrt(nC)-1) over chunks (:226-228). */
 int sr_ct_palmer_finalize(const double* d_S, int nC, long long nF, int nR, long long L, float* d_Ct,
                           float* d_dCt, void* stream);

@@ -30,7 +30,6 @@ def _declare(lib):
         "sr_ct_lag_sums": (i, [vp, ll, i, ll, i, ll, vp, vp]),
         "sr_pack_vectors_f32_chunks": (i, [vp, i, i, i, ll, i, dp, vp, ll, vp]),
         "sr_ct_lag_sums_chunks": (i, [vp, ll, i, i, i, ll, i, ll, vp, vp]),
-        "sr_ct_lag_sums_variant": (i, [vp, ll, i, ll, i, ll, vp, i, vp]),
         "sr_ct_palmer_finalize": (i, [vp, i, ll, i, ll, vp, vp, vp]),
         "sr_ct_palmer_device": (i, [vp, i, ll, i, vp, vp, vp, sz, vp]),
         "sr_ct_palmer_host": (i, [vp, i, ll, i, vp, vp]),

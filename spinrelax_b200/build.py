@@ -33,7 +33,8 @@ def _digest():
     h = hashlib.sha256()
     files = _sources() + sorted(
         os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))
-    ) + [os.path.join(HERE, "..", "include", "spinrelax_b200.h")]
+    ) + sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".inc")) + \
+        [os.path.join(HERE, "..", "include", "spinrelax_b200.h")]
     for p in files:
         with open(p, "rb") as fp:
             h.update(p.encode())
@@ -57,6 +58,28 @@ def _compile_one(args):
     return src, res.returncode, res.stdout + res.stderr
 
 
+def build_tuning(out, sources=("ct.cu", "api.cu"), verbose=False):
+    """Tuning build (-DSR_TUNING): the experimental K1 configurations + sr_ct_lag_sums_variant, linked into `out`
+    (a path outside the package; tools/tune_ct.py).  Never loaded by the product."""
+    objs = []
+    for name in sources:
+        obj = out + "." + name[:-3] + ".o"
+        cmd = [nvcc_path()] + NVCC_FLAGS + ["-DSR_TUNING"] + (["-Xptxas", "-v"] if verbose else []) + \
+            ["-c", "-o", obj, os.path.join(CSRC, name)]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if verbose or res.returncode != 0:
+            sys.stderr.write(res.stdout + res.stderr)
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed on %s (tuning build)" % name)
+        objs.append(obj)
+    res = subprocess.run([nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", out] + objs,
+                         capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("nvcc failed linking the tuning library")
+    return out
+
+
 def build(force=False, verbose=False):
     """Compile every .cu under csrc/ (in parallel) and link them into one shared library. Returns its path."""
     from concurrent.futures import ThreadPoolExecutor
@@ -65,6 +88,8 @@ def build(force=False, verbose=False):
         with open(STAMP) as fp:
             if fp.read().strip() == dig:
                 return LIB
+    if not os.path.exists(nvcc_path()) and os.path.sep in nvcc_path():
+        raise RuntimeError("libspinrelax_b200.so is missing or stale and nvcc is not available to rebuild it")
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
     jobs = [(s, os.path.join(objdir, os.path.basename(s)[:-3] + ".o"), verbose) for s in _sources()]

@@ -23,28 +23,104 @@ namespace {
 // frame per step (static circular indexing, fully unrolled over R), so one step costs
 // 6 LDS.32 + 4R FMA-pipe instructions.
 // ------------------------------------------------------------------------------------------------
-// Tile geometry is a compile-time configuration; kLongVariant / kShortVariant are what the product launches,
-// the other instantiations exist so that tools/tune_ct.py can time them on the GPU.
-template <int R_, int MB_, int FB_, int NW_, int MINB_, int NS_ = 2>
+// Tile geometry is a compile-time configuration; kLong / kShort are what the product launches.  Building with
+// -DSR_TUNING (tools/build_tune.py -> tools/libct_tune.so, never the product library) adds the table of experimental
+// configurations and the entry point sr_ct_lag_sums_variant that tools/tune_ct.py times on the GPU.
+//
+// FLUSH selects how the FP32 partial sums reach the FP64 lag sums:
+//   0  block flush: every FB blocks all R partial sums are converted and added to FP64 accumulators held in
+//      registers, then zeroed (R x (F2F + DADD + MOV) in one burst);
+//   1  staggered flush, FP64 accumulators in registers: in the last block of every FB, iteration kk of the unrolled
+//      window loop flushes partial sum kk and restarts it with a plain multiply (the FFMA of that term becomes an
+//      FMUL, so the reset costs nothing) -- one F2F + DADD per step instead of a burst, no MOVs;
+//   2  staggered flush, FP64 accumulators in shared memory (one array of TL doubles per warp): frees 2R registers
+//      per thread for a wider window (R up to 33 at 12 warps), at one LDS.64 + STS.64 per flushed sum.
+// DIAG (tuning builds only) removes pieces of the loop to attribute their cost: 1 no flush, 2 no window loads,
+// 3 no left-vector loads, 4 no shared-memory loads at all.  Results are wrong by construction.
+template <int R_, int MB_, int FB_, int NW_, int MINB_, int NS_ = 2, int FLUSH_ = 0, int DIAG_ = 0, int ORDER_ = 0>
 struct CtCfg {
+  static constexpr int ORDER = ORDER_;    // 0: lag after lag; 1: in phases (R multiplies, R + R dot FMAs, R accumulates); 2: phases, order pinned
   static constexpr int NS = NS_;          // TMA stages in the ring
   static constexpr int R = R_;            // lags per lane (odd)
   static constexpr int MB = MB_;          // R-step blocks per warp per frame tile
   static constexpr int FB = FB_;          // blocks between FP32 -> FP64 flushes (R*FB terms per FP32 partial sum)
   static constexpr int NW = NW_;          // warps per CTA
   static constexpr int MINB = MINB_;      // CTAs per SM promised to the compiler
+  static constexpr int FLUSH = FLUSH_;
+  static constexpr int DIAG = DIAG_;
   static constexpr int TFW = R * MB;      // frames per warp per tile
   static constexpr int TF = NW * TFW;     // frames per tile
   static constexpr int TL = 32 * R;       // lags per tile
   static constexpr int TW = TF + TL;      // window frames per tile
   static constexpr int StageFloats = 3 * TF + 3 * TW;   // LX LY LZ WX WY WZ
   static constexpr int StageBytes = StageFloats * 4;
-  static constexpr int SmemBytes = NS * StageBytes;
+  static constexpr int AccBytes = FLUSH == 2 ? NW * TL * 8 : 0;   // per-warp FP64 lag sums in shared memory
+  static constexpr int SmemBytes = NS * StageBytes + AccBytes;
   static_assert(R % 2 == 1, "R must be odd: lane stride of the window loads has to be conflict free");
   static_assert(MB % FB == 0, "flush interval must divide the warp tile");
   static_assert(TF % 4 == 0 && TL % 4 == 0, "TMA sources and destinations must stay 16-byte aligned");
-  static_assert(NW * TL * 8 <= SmemBytes, "epilogue reduction buffer must fit in the stage buffers");
+  static_assert(NW * TL * 8 <= NS * StageBytes, "epilogue reduction buffer must fit in the stage buffers");
+  static_assert(StageBytes % 16 == 0, "the FP64 accumulator arrays follow the stages and must stay aligned");
 };
+
+// One block of R steps for one lane: R x R (left frame, lag) pairs.  DOFLUSH: this is the last block of a flush
+// interval (modes 1 and 2).
+template <class Cfg, bool DOFLUSH>
+__device__ __forceinline__ void ct_block(const float* __restrict__ LX, const float* __restrict__ LY,
+                                         const float* __restrict__ LZ, const float* __restrict__ WX,
+                                         const float* __restrict__ WY, const float* __restrict__ WZ, int s, int o,
+                                         float (&wx)[Cfg::R], float (&wy)[Cfg::R], float (&wz)[Cfg::R],
+                                         float (&acc)[Cfg::R], double (&acc64)[Cfg::FLUSH == 2 ? 1 : Cfg::R],
+                                         double* __restrict__ sacc) {
+  constexpr int kR = Cfg::R;
+#pragma unroll
+  for (int kk = 0; kk < kR; ++kk) {
+    float ax, ay, az, nx, ny, nz;
+    if (Cfg::DIAG == 3 || Cfg::DIAG == 4) { ax = wx[(kk + 1) % kR]; ay = wy[(kk + 2) % kR]; az = wz[(kk + 3) % kR]; }
+    else { ax = LX[s + kk]; ay = LY[s + kk]; az = LZ[s + kk]; }                  // u(t), broadcast
+    const int iw = s + kk + o + kR;                                              // frame entering the window
+    if (Cfg::DIAG == 2 || Cfg::DIAG == 4) { nx = wx[kk] + 1e-7f; ny = wy[kk]; nz = wz[kk]; }
+    else { nx = WX[iw]; ny = WY[iw]; nz = WZ[iw]; }
+    if (DOFLUSH && Cfg::DIAG != 1) {
+      if (Cfg::FLUSH == 1) acc64[kk] += (double)acc[kk];
+      if (Cfg::FLUSH == 2) sacc[o + kk] += (double)acc[kk];
+    }
+    if (Cfg::ORDER == 0) {
+#pragma unroll
+      for (int j = 0; j < kR; ++j) {
+        const int sl = (kk + j) % kR;              // slot holding frame t + d0 + o + j
+        float d = ax * wx[sl];
+        d = fmaf(ay, wy[sl], d);
+        d = fmaf(az, wz[sl], d);
+        if (DOFLUSH && j == kk) acc[j] = d * d;    // partial sum kk was just flushed: restart it
+        else acc[j] = fmaf(d, d, acc[j]);
+      }
+    } else {
+      // the same arithmetic in four phases: within a phase the left component sits in the operand-reuse cache
+      float d[kR];
+      if (Cfg::ORDER == 1) {
+#pragma unroll
+        for (int j = 0; j < kR; ++j) d[j] = ax * wx[(kk + j) % kR];
+#pragma unroll
+        for (int j = 0; j < kR; ++j) d[j] = fmaf(ay, wy[(kk + j) % kR], d[j]);
+#pragma unroll
+        for (int j = 0; j < kR; ++j) d[j] = fmaf(az, wz[(kk + j) % kR], d[j]);
+#pragma unroll
+        for (int j = 0; j < kR; ++j) acc[j] = fmaf(d[j], d[j], acc[j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < kR; ++j) asm volatile("mul.rn.f32 %0, %1, %2;" : "=f"(d[j]) : "f"(ax), "f"(wx[(kk + j) % kR]));
+#pragma unroll
+        for (int j = 0; j < kR; ++j) asm volatile("fma.rn.f32 %0, %1, %2, %0;" : "+f"(d[j]) : "f"(ay), "f"(wy[(kk + j) % kR]));
+#pragma unroll
+        for (int j = 0; j < kR; ++j) asm volatile("fma.rn.f32 %0, %1, %2, %0;" : "+f"(d[j]) : "f"(az), "f"(wz[(kk + j) % kR]));
+#pragma unroll
+        for (int j = 0; j < kR; ++j) asm volatile("fma.rn.f32 %0, %1, %1, %0;" : "+f"(acc[j]) : "f"(d[j]));
+      }
+    }
+    wx[kk] = nx; wy[kk] = ny; wz[kk] = nz;
+  }
+}
 
 template <class Cfg>
 __global__ void __launch_bounds__(Cfg::NW * 32, Cfg::MINB)
@@ -74,6 +150,9 @@ ct_lag_kernel(const float* __restrict__ U, long long pitch, int nF, int L, int n
     for (int i = 0; i < kNS; ++i) { sr_mbar_init(&full_bar[i], 1); sr_mbar_init(&empty_bar[i], kNW); }
     sr_fence_barrier_init();
   }
+  double* const sacc_all = reinterpret_cast<double*>(smem_raw + (size_t)kNS * kStageBytes);
+  if (Cfg::FLUSH == 2)
+    for (int i = tid; i < kNW * kTL; i += kNW * 32) sacc_all[i] = 0.0;
   __syncthreads();
 
   auto issue = [&](int k, int st) {
@@ -88,9 +167,13 @@ ct_lag_kernel(const float* __restrict__ U, long long pitch, int nF, int L, int n
     sr_tma_load_1d(sb + 3 * kTF + 2 * kTW, rowZ + f + d0, kTW * 4, &full_bar[st]);
   };
 
-  double acc64[kR];
+  double acc64[Cfg::FLUSH == 2 ? 1 : kR];
 #pragma unroll
-  for (int j = 0; j < kR; ++j) acc64[j] = 0.0;
+  for (int j = 0; j < (Cfg::FLUSH == 2 ? 1 : kR); ++j) acc64[j] = 0.0;
+  float acc[kR];                      // FP32 partial sums; with a staggered flush they live across blocks and tiles
+#pragma unroll
+  for (int j = 0; j < kR; ++j) acc[j] = 0.f;
+  double* const sacc = sacc_all + warp * kTL;
 
   // Ring of kNS stages.  Thread 0 is the producer: before tile k it refills the stage that tile k-1 used
   // (tile k + kNS - 1), waiting on that stage's "empty" barrier (one arrival per warp).  Consumer warps
@@ -128,43 +211,48 @@ ct_lag_kernel(const float* __restrict__ U, long long pitch, int nF, int L, int n
       }
 #pragma unroll 1
       for (int b = 0; b < kMB; b += kFB) {
-        float acc[kR];
+        if (Cfg::FLUSH == 0 && Cfg::DIAG != 1) {
+          float accb[kR];                    // partial sums of this flush interval only
 #pragma unroll
-        for (int j = 0; j < kR; ++j) acc[j] = 0.f;
+          for (int j = 0; j < kR; ++j) accb[j] = 0.f;
 #pragma unroll 1
-        for (int bb = 0; bb < kFB; ++bb) {
-          const int s = s0 + (b + bb) * kR;
+          for (int bb = 0; bb < kFB; ++bb)
+            ct_block<Cfg, false>(LX, LY, LZ, WX, WY, WZ, s0 + (b + bb) * kR, o, wx, wy, wz, accb, acc64, sacc);
 #pragma unroll
-          for (int kk = 0; kk < kR; ++kk) {
-            const float ax = LX[s + kk], ay = LY[s + kk], az = LZ[s + kk];   // u(t), broadcast
-            const int iw = s + kk + o + kR;                                  // frame entering the window
-            const float nx = WX[iw], ny = WY[iw], nz = WZ[iw];
-#pragma unroll
-            for (int j = 0; j < kR; ++j) {
-              const int sl = (kk + j) % kR;              // slot holding frame t + d0 + o + j
-              float d = ax * wx[sl];
-              d = fmaf(ay, wy[sl], d);
-              d = fmaf(az, wz[sl], d);
-              acc[j] = fmaf(d, d, acc[j]);
-            }
-            wx[kk] = nx; wy[kk] = ny; wz[kk] = nz;
-          }
+          for (int j = 0; j < kR; ++j) acc64[j] += (double)accb[j];
+        } else if (Cfg::FLUSH == 0) {
+#pragma unroll 1
+          for (int bb = 0; bb < kFB; ++bb)
+            ct_block<Cfg, false>(LX, LY, LZ, WX, WY, WZ, s0 + (b + bb) * kR, o, wx, wy, wz, acc, acc64, sacc);
+        } else {
+#pragma unroll 1
+          for (int bb = 0; bb < kFB - 1; ++bb)
+            ct_block<Cfg, false>(LX, LY, LZ, WX, WY, WZ, s0 + (b + bb) * kR, o, wx, wy, wz, acc, acc64, sacc);
+          ct_block<Cfg, true>(LX, LY, LZ, WX, WY, WZ, s0 + (b + kFB - 1) * kR, o, wx, wy, wz, acc, acc64, sacc);
         }
-#pragma unroll
-        for (int j = 0; j < kR; ++j) acc64[j] += (double)acc[j];
       }
     }
     __syncwarp();
     if (lane == 0) sr_mbar_arrive(&empty_bar[st]);
     if (++st == kNS) { st = 0; ph ^= 1; }
   }
+  if (Cfg::FLUSH != 0 || Cfg::DIAG == 1) {   // what the partial sums still hold after the last flush
+#pragma unroll
+    for (int j = 0; j < kR; ++j) {
+      if (Cfg::FLUSH == 2) sacc[o + j] += (double)acc[j];
+      else acc64[j] += (double)acc[j];
+    }
+  }
   __syncthreads();
 
-  // cross-warp reduction through the (now idle) stage buffers, one store per lag
-  double* red = reinterpret_cast<double*>(smem_raw);
+  // cross-warp reduction, one store per lag: through the (now idle) stage buffers, or straight from the per-warp
+  // shared-memory accumulators
+  double* red = Cfg::FLUSH == 2 ? sacc_all : reinterpret_cast<double*>(smem_raw);
+  if (Cfg::FLUSH != 2) {
 #pragma unroll
-  for (int j = 0; j < kR; ++j) red[warp * kTL + o + j] = acc64[j];
-  __syncthreads();
+    for (int j = 0; j < kR; ++j) red[warp * kTL + o + j] = acc64[j];
+    __syncthreads();
+  }
   for (int i = tid; i < kTL; i += kNW * 32) {
     double s = 0.0;
 #pragma unroll
@@ -301,36 +389,21 @@ ct_finalize_kernel(const double* __restrict__ S, int nC, int nF, int nR, int L, 
 // ================================================================================================
 // C ABI
 // ================================================================================================
-// variants (R, MB, FB, NW, CTAs/SM, stages); tools/tune_ct.py times them.  The product path launches
-// kLongVariant for long chunks and kShortVariant (smaller lag / frame tiles) for short ones.
-using CtV0 = CtCfg<15, 8, 1, 8, 2, 2>;
-using CtV1 = CtCfg<15, 8, 2, 8, 2, 2>;
-using CtV2 = CtCfg<15, 8, 4, 8, 2, 2>;
-using CtV3 = CtCfg<19, 6, 2, 12, 1, 2>;
-using CtV4 = CtCfg<19, 6, 2, 12, 1, 3>;
-using CtV5 = CtCfg<15, 8, 2, 8, 2, 3>;
-using CtV6 = CtCfg<17, 8, 2, 8, 2, 3>;
-using CtV7 = CtCfg<15, 12, 2, 8, 2, 3>;
-using CtV8 = CtCfg<21, 4, 2, 12, 1, 3>;
-using CtV9 = CtCfg<19, 4, 2, 12, 1, 4>;
-using CtV10 = CtCfg<19, 6, 1, 12, 1, 3>;
-using CtV11 = CtCfg<17, 6, 2, 12, 1, 3>;
-using CtV12 = CtCfg<15, 8, 1, 8, 2, 3>;
-using CtV13 = CtCfg<19, 6, 3, 12, 1, 4>;
-using CtV14 = CtCfg<19, 9, 3, 12, 1, 3>;
-using CtV15 = CtCfg<19, 6, 3, 12, 1, 3>;
-using CtV16 = CtCfg<19, 12, 3, 12, 1, 3>;
-using CtV17 = CtCfg<19, 12, 3, 12, 1, 2>;
-constexpr int kNumVariants = 18;
-constexpr int kLongVariant = 17;     // R = 19, 12 warps, 1 CTA/SM, 2 stages of 2736 frames: 57 terms per FP32 partial sum
-constexpr int kShortVariant = 12;    // R = 15, 8 warps, 2 CTAs/SM, 3 stages: 15 terms per FP32 partial sum (few chunk
-                                     // means enter dCt when chunks are short, so keep its rounding at the 1e-7 level)
+// The product launches kLong for long chunks and kShort (smaller lag / frame tiles) for short ones.
+using CtLong = CtCfg<19, 12, 3, 12, 1, 2>;     // R = 19, 12 warps, 1 CTA/SM, 2 stages of 2736 frames: 57 terms per FP32 partial sum
+using CtShort = CtCfg<15, 8, 1, 8, 2, 3>;      // R = 15, 8 warps, 2 CTAs/SM, 3 stages: 15 terms per FP32 partial sum (few chunk
+                                               // means enter dCt when chunks are short, so keep its rounding at the 1e-7 level)
 constexpr long long kShortFrames = 8192;
-constexpr int kMaxTF = 2736, kMaxTL = 32 * 21;   // padding must cover the largest tile of any variant
+#ifdef SR_TUNING
+constexpr int kMaxTF = 2736, kMaxTL = 32 * 45;
+#else
+constexpr int kMaxTF = 2736, kMaxTL = 32 * 19;   // padding must cover the largest tile of any configuration
+#endif
 
 template <class Cfg>
 int launch_ct_lag(const float* U, long long pitch, long long nF, int nR, int nC, int c0, int nCsub, long long L, double* S,
                   cudaStream_t st) {
+  static_assert(Cfg::TF <= kMaxTF && Cfg::TL <= kMaxTL, "zero padding of the packed rows must cover this tile");
   const long long nLT = (L + Cfg::TL) / Cfg::TL;   // tiles start at lag 0: ceil((L + 1) / TL)
   const long long items = (long long)nR * nCsub * nLT;
   SR_REQUIRE(items < (1LL << 31), "sr_ct_lag_sums: %lld work items exceed the grid limit", items);
@@ -388,8 +461,8 @@ extern "C" int sr_pack_vectors_f32(const float* d_vecs, int nC, long long nF, in
   return sr_pack_vectors_f32_chunks(d_vecs, nC, 0, nC, nF, nR, h_q_rot, d_packed, pitch, stream);
 }
 
-static int ct_lag_sums_impl(const void* d_packed, long long pitch, int nC, int c0, int nCsub, long long nF, int nR,
-                            long long L, double* d_S, int variant, void* stream) {
+static int ct_lag_sums_check(const void* d_packed, long long pitch, int nC, int c0, int nCsub, long long nF, int nR,
+                             long long L, double* d_S) {
   SR_REQUIRE(d_packed && d_S, "sr_ct_lag_sums: null pointer");
   SR_REQUIRE(nC > 0 && nR > 0 && nF >= 2, "sr_ct_lag_sums: bad shape (nC=%d nF=%lld nR=%d)", nC, nF, nR);
   SR_REQUIRE(L >= 1 && L <= nF - 1, "sr_ct_lag_sums: L=%lld outside [1, nF-1]", L);
@@ -398,49 +471,33 @@ static int ct_lag_sums_impl(const void* d_packed, long long pitch, int nC, int c
              kMaxTF + kMaxTL);
   SR_REQUIRE((long long)nR * nC < (1LL << 31), "sr_ct_lag_sums: too many (vector, chunk) rows");
   SR_REQUIRE(pitch % 4 == 0 && ((uintptr_t)d_packed & 15) == 0, "sr_ct_lag_sums: packed stream must be 16-byte aligned with pitch %% 4 == 0");
-  const float* U = (const float*)d_packed;
-  cudaStream_t st = (cudaStream_t)stream;
   SR_REQUIRE(c0 >= 0 && nCsub > 0 && c0 + nCsub <= nC, "sr_ct_lag_sums: chunk range [%d, %d) outside [0, %d)", c0, c0 + nCsub, nC);
-  switch (variant) {
-    case 0: return launch_ct_lag<CtV0>(U, pitch, nF, nR, nC, c0, nCsub, L, d_S, st);
-    case 1: return launch_ct_lag<CtV1>(U, pitch, nF, nR, nC, c0, nCsub, L, d_S, st);
-    case 2: return launch_ct_lag<CtV2>(U, pitch, nF, nR, nC, c0, nCsub, L, d_S, st);
-    case 3: return launch_ct_lag<CtV3>(U, pitch, nF, nR, nC, c0, nCsub, L, d_S, st);
-    case 4: return launch_ct_lag<CtV4>(U, pitch, nF, nR, nC, c0, nCsub, L, d_S, st);
-    case 5: return launch_ct_lag<CtV5>(U, pitch, nF, nR, nC, c0, nCsub, L, d_S, st);
-    case 6: return launch_ct_lag<CtV6>(U, pitch, nF, nR, nC, c0, nCsub, L, d_S, st);
-    case 7: return launch_ct_lag<CtV7>(U, pitch, nF, nR, nC, c0, nCsub, L, d_S, st);
-    case 8: return launch_ct_lag<CtV8>(U, pitch, nF, nR, nC, c0, nCsub, L, d_S, st);
-    case 9: return launch_ct_lag<CtV9>(U, pitch, nF, nR, nC, c0, nCsub, L, d_S, st);
-    case 10: return launch_ct_lag<CtV10>(U, pitch, nF, nR, nC, c0, nCsub, L, d_S, st);
-    case 11: return launch_ct_lag<CtV11>(U, pitch, nF, nR, nC, c0, nCsub, L, d_S, st);
-    case 12: return launch_ct_lag<CtV12>(U, pitch, nF, nR, nC, c0, nCsub, L, d_S, st);
-    case 13: return launch_ct_lag<CtV13>(U, pitch, nF, nR, nC, c0, nCsub, L, d_S, st);
-    case 14: return launch_ct_lag<CtV14>(U, pitch, nF, nR, nC, c0, nCsub, L, d_S, st);
-    case 15: return launch_ct_lag<CtV15>(U, pitch, nF, nR, nC, c0, nCsub, L, d_S, st);
-    case 16: return launch_ct_lag<CtV16>(U, pitch, nF, nR, nC, c0, nCsub, L, d_S, st);
-    case 17: return launch_ct_lag<CtV17>(U, pitch, nF, nR, nC, c0, nCsub, L, d_S, st);
-    default: break;
-  }
-  sr_set_error("sr_ct_lag_sums_variant: unknown variant %d (have %d)", variant, kNumVariants);
-  return SR_ERR_ARG;
+  return SR_OK;
 }
 
-extern "C" int sr_ct_lag_sums_variant(const void* d_packed, long long pitch, int nC, long long nF, int nR, long long L,
-                                      double* d_S, int variant, void* stream) {
-  return ct_lag_sums_impl(d_packed, pitch, nC, 0, nC, nF, nR, L, d_S, variant, stream);
+static int ct_lag_sums_impl(const void* d_packed, long long pitch, int nC, int c0, int nCsub, long long nF, int nR,
+                            long long L, double* d_S, void* stream) {
+  const int rc = ct_lag_sums_check(d_packed, pitch, nC, c0, nCsub, nF, nR, L, d_S);
+  if (rc) return rc;
+  const float* U = (const float*)d_packed;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (nF < kShortFrames) return launch_ct_lag<CtShort>(U, pitch, nF, nR, nC, c0, nCsub, L, d_S, st);
+  return launch_ct_lag<CtLong>(U, pitch, nF, nR, nC, c0, nCsub, L, d_S, st);
 }
+
+#ifdef SR_TUNING
+// Experimental configurations (R, MB, FB, NW, CTAs/SM, stages, FLUSH, DIAG), timed by tools/tune_ct.py.
+#include "ct_tuning_variants.inc"
+#endif
 
 extern "C" int sr_ct_lag_sums(const void* d_packed, long long pitch, int nC, long long nF, int nR, long long L,
                               double* d_S, void* stream) {
-  return ct_lag_sums_impl(d_packed, pitch, nC, 0, nC, nF, nR, L, d_S, nF < kShortFrames ? kShortVariant : kLongVariant,
-                          stream);
+  return ct_lag_sums_impl(d_packed, pitch, nC, 0, nC, nF, nR, L, d_S, stream);
 }
 
 extern "C" int sr_ct_lag_sums_chunks(const void* d_packed, long long pitch, int nC, int c0, int nCsub, long long nF, int nR,
                                      long long L, double* d_S, void* stream) {
-  return ct_lag_sums_impl(d_packed, pitch, nC, c0, nCsub, nF, nR, L, d_S,
-                          nF < kShortFrames ? kShortVariant : kLongVariant, stream);
+  return ct_lag_sums_impl(d_packed, pitch, nC, c0, nCsub, nF, nR, L, d_S, stream);
 }
 
 extern "C" int sr_ct_palmer_finalize(const double* d_S, int nC, long long nF, int nR, long long L, float* d_Ct,
