@@ -557,12 +557,23 @@ struct HostCallCache {
     d_buf = nullptr; d_cap = stage_cap = 0; copy = comp = nullptr; device = -1;
   }
 };
-HostCallCache g_host_cache;
+// one cache per device: host threads that each drive their own GPU (spinrelax_b200/multigpu.py) do not serialise on
+// a shared lock, and switching devices does not throw the buffers away
+constexpr int kMaxDevices = 16;
+HostCallCache g_host_cache[kMaxDevices];
 }  // namespace
 
 extern "C" void sr_release_host_cache(void) {
-  std::lock_guard<std::mutex> lock(g_host_cache.mu);
-  g_host_cache.release();
+  int cur = 0;
+  cudaGetDevice(&cur);
+  for (int d = 0; d < kMaxDevices; ++d) {
+    std::lock_guard<std::mutex> lock(g_host_cache[d].mu);
+    if (g_host_cache[d].device >= 0) {
+      cudaSetDevice(g_host_cache[d].device);
+      g_host_cache[d].release();
+    }
+  }
+  cudaSetDevice(cur);
 }
 
 extern "C" int sr_ct_palmer_host(const float* h_vecs, int nC, long long nF, int nR, float* h_Ct, float* h_dCt) {
@@ -576,16 +587,17 @@ extern "C" int sr_ct_palmer_host(const float* h_vecs, int nC, long long nF, int 
   const size_t need = in_bytes + 2 * out_bytes + ws_bytes;
   const size_t stage_bytes = (size_t)32 << 20;
   const long long pitch = sr_ct_row_pitch(nF);
-  HostCallCache& hc = g_host_cache;
-  std::lock_guard<std::mutex> lock(hc.mu);
   int rc = SR_OK, dev = 0;
   cudaError_t e = cudaSuccess;
+  SR_CUDA(cudaGetDevice(&dev));
+  SR_REQUIRE(dev >= 0 && dev < kMaxDevices, "sr_ct_palmer_host: device index %d outside [0, %d)", dev, kMaxDevices);
+  HostCallCache& hc = g_host_cache[dev];
+  std::lock_guard<std::mutex> lock(hc.mu);
   auto fail = [&](const char* what) {
     sr_set_error("sr_ct_palmer_host: %s failed: %s", what, cudaGetErrorString(e));
     rc = SR_ERR_CUDA;
   };
-  SR_CUDA(cudaGetDevice(&dev));
-  if (hc.device != dev) { hc.release(); hc.device = dev; }
+  hc.device = dev;
   if (hc.d_cap < need) {
     if (hc.d_buf) cudaFree(hc.d_buf);
     hc.d_buf = nullptr; hc.d_cap = 0;

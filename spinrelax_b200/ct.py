@@ -119,9 +119,27 @@ def calculate_Ct_Palmer(vecs, _verbose=True):
     dCt = np.empty((L, nR), dtype=np.float32)
     if L == 0:
         return Ct.astype(out_dtype), dCt.astype(out_dtype)
-    rc = lib.sr_ct_palmer_host(v32.ctypes.data_as(ctypes.c_void_p), nC, nF, nR,
-                               Ct.ctypes.data_as(ctypes.c_void_p), dCt.ctypes.data_as(ctypes.c_void_p))
-    _lib.check(rc, "sr_ct_palmer_host")
+    from . import multigpu
+    blocks = multigpu.plan(nR)
+    if len(blocks) == 1:
+        with _lib.require_cuda().cuda.device(blocks[0][0]):
+            rc = lib.sr_ct_palmer_host(v32.ctypes.data_as(ctypes.c_void_p), nC, nF, nR,
+                                       Ct.ctypes.data_as(ctypes.c_void_p), dCt.ctypes.data_as(ctypes.c_void_p))
+            _lib.check(rc, "sr_ct_palmer_host")
+        return Ct.astype(out_dtype, copy=False), dCt.astype(out_dtype, copy=False)
+
+    # bond vectors are independent (:222-228): every selected GPU takes a contiguous block of them through the same
+    # host-buffer entry point, on its own host thread
+    def work(dev, a, b):
+        sub = np.ascontiguousarray(v32[:, :, a:b, :])
+        c, d = np.empty((L, b - a), dtype=np.float32), np.empty((L, b - a), dtype=np.float32)
+        rc = lib.sr_ct_palmer_host(sub.ctypes.data_as(ctypes.c_void_p), nC, nF, b - a,
+                                   c.ctypes.data_as(ctypes.c_void_p), d.ctypes.data_as(ctypes.c_void_p))
+        _lib.check(rc, "sr_ct_palmer_host (device %d)" % dev)
+        return c, d
+
+    for (dev, a, b), (c, d) in zip(blocks, multigpu.run(blocks, work)):
+        Ct[:, a:b], dCt[:, a:b] = c, d
     return Ct.astype(out_dtype, copy=False), dCt.astype(out_dtype, copy=False)
 
 
@@ -129,14 +147,20 @@ def _block_moments(vecs3, frames_per_block):
     """GPU sums of x,y,z and the six second moments per (block, vector): (nBlocks, nR, 9) float64."""
     torch = _lib.require_cuda()
     lib = _lib.load()
-    v = np.ascontiguousarray(vecs3, dtype=np.float32)
+    from . import multigpu
+    v = np.asarray(vecs3, dtype=np.float32)
     nFr, nR, _ = v.shape
     nB = -(-nFr // frames_per_block)
-    vd = torch.from_numpy(v).cuda()
-    out = torch.empty((nB, nR, 9), dtype=torch.float64, device=vd.device)
-    _lib.check(lib.sr_vec_block_moments(vd.data_ptr(), nFr, nR, int(frames_per_block), out.data_ptr(),
-                                        _lib.current_stream_ptr()), "sr_vec_block_moments")
-    return out.cpu().numpy()
+
+    def work(dev, a, b):
+        vd = torch.from_numpy(np.ascontiguousarray(v[:, a:b, :])).cuda()
+        out = torch.empty((nB, b - a, 9), dtype=torch.float64, device=vd.device)
+        _lib.check(lib.sr_vec_block_moments(vd.data_ptr(), nFr, b - a, int(frames_per_block), out.data_ptr(),
+                                            _lib.current_stream_ptr()), "sr_vec_block_moments")
+        return out.cpu().numpy()
+
+    blocks = multigpu.plan(nR)
+    return np.concatenate(multigpu.run(blocks, work), axis=1)
 
 
 def _s2_from_moments(m, n):

@@ -43,18 +43,25 @@ def dq_moment_sums(q, lags, nchunk=1):
     if lags.size == 0 or lags.min() < 1 or lags.max() >= N:
         raise ValueError("dq_moment_sums: lags must lie in [1, N)")
     nCh = max(1, int(nchunk))
-    qd = torch.from_numpy(q32).cuda()
-    ld = torch.from_numpy(lags).cuda()
-    M = torch.empty((lags.size, nCh, 6), dtype=torch.float64, device=qd.device)
-    for r in range(nRep):
-        _lib.check(lib.sr_dq_moments_pooled(qd[r].data_ptr(), N, ld.data_ptr(), lags.size, int(lags.min()), nCh, r, nRep,
-                                            1 if r > 0 else 0, M.data_ptr(), _lib.current_stream_ptr()),
-                   "sr_dq_moments_pooled")
+    from . import multigpu
+
+    def work(dev, a, b):        # every device holds the (small) trajectory and reduces a block of the lag list
+        sub = np.ascontiguousarray(lags[a:b])
+        qd = torch.from_numpy(q32).cuda()
+        ld = torch.from_numpy(sub).cuda()
+        M = torch.empty((sub.size, nCh, 6), dtype=torch.float64, device=qd.device)
+        for r in range(nRep):
+            _lib.check(lib.sr_dq_moments_pooled(qd[r].data_ptr(), N, ld.data_ptr(), sub.size, int(sub.min()), nCh, r, nRep,
+                                                1 if r > 0 else 0, M.data_ptr(), _lib.current_stream_ptr()),
+                       "sr_dq_moments_pooled")
+        return M.cpu().numpy()
+
+    M = np.concatenate(multigpu.run(multigpu.plan(lags.size, min_per_device=64), work), axis=0)
     n = (N - lags) * nRep
     nb = -(-n // nCh)
     k = np.arange(nCh)[None, :]
     counts = np.clip(np.minimum(n[:, None], nb[:, None] * (k + 1)) - nb[:, None] * k, 0, None)
-    return M.cpu().numpy(), n, counts
+    return M, n, counts
 
 
 def dq_histogram3d(q, delta, nbins=101):

@@ -35,34 +35,43 @@ KERNEL_EVENTS = None      # set to a list to collect (start, end) CUDA event pai
 
 def _device_solve(t, y, sigma, p0, lo, hi):
     """sr_ct_fit_trf on (nR, L) curves: returns popt (nR,nP), the R factor of the Jacobian at the solution (nR,nP,nP),
-    cost (nR,) and status (nR,2) = (SciPy termination status, nfev)."""
+    cost (nR,) and status (nR,2) = (SciPy termination status, nfev).  Residues are independent: with several GPUs
+    selected (multigpu.devices) every device solves a contiguous block of them."""
     torch = _lib.require_cuda()
     lib = _lib.load()
-    dev = torch.device("cuda")
-    f = lambda a: torch.from_numpy(np.array(a, dtype=np.float64, order='C')).to(dev)   # noqa: E731
+    from . import multigpu
     nR, L = y.shape
     nP = p0.shape[1]
-    td, yd, p0d, lod, hid = f(np.broadcast_to(t, (nR, L))), f(y), f(p0), f(np.broadcast_to(lo, (nR, nP))), \
-        f(np.broadcast_to(hi, (nR, nP)))
-    sd = None if sigma is None else f(np.broadcast_to(sigma, (nR, L)))
-    popt = torch.empty((nR, nP), dtype=torch.float64, device=dev)
-    R = torch.empty((nR, nP, nP), dtype=torch.float64, device=dev)
-    cost = torch.empty(nR, dtype=torch.float64, device=dev)
-    status = torch.empty((nR, 2), dtype=torch.int32, device=dev)
-    wbytes = int(lib.sr_ct_fit_workspace_bytes(nR, L, nP))
-    work = torch.empty(max(wbytes, 8) // 8, dtype=torch.float64, device=dev) if wbytes else None
-    if KERNEL_EVENTS is not None:
-        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-        ev[0].record()
-    _lib.check(lib.sr_ct_fit_trf(td.data_ptr(), yd.data_ptr(), 0 if sd is None else sd.data_ptr(), nR, L, nP,
-                                 p0d.data_ptr(), lod.data_ptr(), hid.data_ptr(), MAX_NFEV, FTOL, XTOL, GTOL,
-                                 popt.data_ptr(), R.data_ptr(), cost.data_ptr(), status.data_ptr(),
-                                 0 if work is None else work.data_ptr(), wbytes, _lib.current_stream_ptr()),
-               "sr_ct_fit_trf")
-    if KERNEL_EVENTS is not None:
-        ev[1].record()
-        KERNEL_EVENTS.append(ev)
-    return popt.cpu().numpy(), R.cpu().numpy(), cost.cpu().numpy(), status.cpu().numpy()
+    t, lo, hi = np.broadcast_to(t, (nR, L)), np.broadcast_to(lo, (nR, nP)), np.broadcast_to(hi, (nR, nP))
+    sigma = None if sigma is None else np.broadcast_to(sigma, (nR, L))
+
+    def work(d, a, b):
+        dev = torch.device("cuda", d)
+        f = lambda x: torch.from_numpy(np.array(x[a:b], dtype=np.float64, order='C')).to(dev)   # noqa: E731
+        n = b - a
+        td, yd, p0d, lod, hid = f(t), f(y), f(p0), f(lo), f(hi)
+        sd = None if sigma is None else f(sigma)
+        popt = torch.empty((n, nP), dtype=torch.float64, device=dev)
+        R = torch.empty((n, nP, nP), dtype=torch.float64, device=dev)
+        cost = torch.empty(n, dtype=torch.float64, device=dev)
+        status = torch.empty((n, 2), dtype=torch.int32, device=dev)
+        wbytes = int(lib.sr_ct_fit_workspace_bytes(n, L, nP))
+        work_buf = torch.empty(max(wbytes, 8) // 8, dtype=torch.float64, device=dev) if wbytes else None
+        if KERNEL_EVENTS is not None:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
+        _lib.check(lib.sr_ct_fit_trf(td.data_ptr(), yd.data_ptr(), 0 if sd is None else sd.data_ptr(), n, L, nP,
+                                     p0d.data_ptr(), lod.data_ptr(), hid.data_ptr(), MAX_NFEV, FTOL, XTOL, GTOL,
+                                     popt.data_ptr(), R.data_ptr(), cost.data_ptr(), status.data_ptr(),
+                                     0 if work_buf is None else work_buf.data_ptr(), wbytes, _lib.current_stream_ptr()),
+                   "sr_ct_fit_trf")
+        if KERNEL_EVENTS is not None:
+            ev[1].record()
+            KERNEL_EVENTS.append(ev)
+        return popt.cpu().numpy(), R.cpu().numpy(), cost.cpu().numpy(), status.cpu().numpy()
+
+    res = multigpu.run(multigpu.plan(nR, min_per_device=32), work)
+    return tuple(np.concatenate([r[k] for r in res], axis=0) for k in range(4))
 
 
 def pcov_from_R(R, cost, L):

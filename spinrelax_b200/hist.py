@@ -123,15 +123,21 @@ def sphere_histogram(frames_vecs, q_rot=None, nbins_phi=72):
     promotes) or float32 (no rotation), edges = [phi edges, cos(theta) edges].
     """
     torch = _lib.require_cuda()
-    v = np.ascontiguousarray(frames_vecs, dtype=np.float32)
+    from . import multigpu
+    v = np.asarray(frames_vecs, dtype=np.float32)
     if v.ndim != 3 or v.shape[-1] != 3:
         raise ValueError("sphere_histogram: expected (frames, nR, 3)")
-    acc = SphereHistogram(v.shape[1], nbins_phi)
-    v_dev = torch.from_numpy(v).to(acc.dev, non_blocking=True)
-    acc.accumulate_device(v_dev, q_rot)
-    counts = acc.finish(v_dev, q_rot)
+
+    def work(dev, a, b):        # every vector has its own histogram: shard the vectors, no reduction
+        acc = SphereHistogram(b - a, nbins_phi, device=torch.device("cuda", dev))
+        v_dev = torch.from_numpy(np.ascontiguousarray(v[:, a:b, :])).to(acc.dev, non_blocking=True)
+        acc.accumulate_device(v_dev, q_rot)
+        return acc.finish(v_dev, q_rot), acc.edges_phi, acc.edges_cos
+
+    res = multigpu.run(multigpu.plan(v.shape[1]), work)
+    counts = np.concatenate([r[0] for r in res], axis=0)
     dtype = np.float64 if q_rot is not None else np.float32
-    return counts.astype(dtype), [acc.edges_phi, acc.edges_cos]
+    return counts.astype(dtype), [res[0][1], res[0][2]]
 
 
 def save_vec_histogram(path, names, hist_list, edges):

@@ -13,7 +13,9 @@ from . import _lib, ct
 
 
 class CtHistStep:
-    def __init__(self, nC, nF, nR, q_rot=None, device=None, world=1, rank=0, hist_bins=72):
+    def __init__(self, nC, nF, nR, q_rot=None, device=None, world=1, rank=0, hist_bins=72, n_total=None):
+        """nR = bond vectors held by THIS rank; n_total = vectors of the whole job (default nR * world), partitioned
+        over the ranks by shard.split_range (so nR must be this rank's share of it)."""
         self.torch = _lib.require_cuda()
         torch = self.torch
         self.lib = _lib.load()
@@ -21,6 +23,14 @@ class CtHistStep:
         self.q_rot = None if q_rot is None else np.asarray(q_rot, dtype=np.float64)
         self.dev = device if device is not None else torch.device("cuda")
         self.world, self.rank = world, rank
+        self.n_total = nR * world if n_total is None else int(n_total)
+        if world > 1:
+            from . import shard
+            if shard.split_sizes(self.n_total, world)[rank] != nR:
+                raise _lib.SpinRelaxError("CtHistStep: rank %d holds %d vectors but the partition of %d over %d ranks "
+                                          "gives it %d" % (rank, nR, self.n_total, world,
+                                                           shard.split_sizes(self.n_total, world)[rank]))
+        self.gathered = self.gathered_hist = None
         self.nbx, self.nby = hist_bins, hist_bins // 2
         self.has_hist = hasattr(self.lib, "sr_sphere_hist") and q_rot is not None
         self.pitch = self.lib.sr_ct_row_pitch(nF)
@@ -65,10 +75,7 @@ class CtHistStep:
                         time_kernels)
             hist = self._hist.finish(v_dev, self.q_rot)     # ambiguous-sample tie-break + D2H of the counts
         if self.world > 1:
-            # every rank owns nR vectors of the global set: gather the (2L, nR) result columns on rank 0
-            from . import shard
-            both = self.torch.cat((self.Ct, self.dCt), dim=0)
-            self.gathered = shard.gather_columns(both, self.nR * self.world, dst=0)
+            self._gather(hist)
         return self.Ct, self.dCt, hist
 
     def run_host(self, v_np):
@@ -118,14 +125,22 @@ class CtHistStep:
             self._hist.accumulate_device(v_dev.view(nC * nF, nR, 3), self.q_rot, reset=True)
             hist = self._hist.finish(v_dev, self.q_rot)
         if self.world > 1:
-            from . import shard
-            both = torch.cat((self.Ct, self.dCt), dim=0)
-            self.gathered = shard.gather_columns(both, self.nR * self.world, dst=0)
+            self._gather(hist)
         main.synchronize()
         out = self._out_host.numpy()          # pinned staging buffer, overwritten by the next call
         if hist is not None:
             hist = hist.astype(np.float64)
         return out[0], out[1], hist
+
+    def _gather(self, hist):
+        """Every rank owns its block of the job's bond vectors: the (2L, nR_local) result columns and the
+        (nR_local, nbx, nby) histogram counts are gathered on rank 0 (no other communication on this path)."""
+        from . import shard
+        both = self.torch.cat((self.Ct, self.dCt), dim=0)
+        self.gathered = shard.gather_columns(both, self.n_total, dst=0)
+        if hist is not None:
+            h = self.torch.from_numpy(np.ascontiguousarray(hist)).to(self.dev)
+            self.gathered_hist = shard.gather_rows(h, self.n_total, dst=0)
 
     # -------------------------------------------------------------------------------------------
     def reset_kernel_timers(self):

@@ -40,6 +40,9 @@ def gather_columns(local, n_total, dst=0):
     import torch.distributed as dist
     world, rank = dist.get_world_size(), dist.get_rank()
     sizes = split_sizes(n_total, world)
+    if local.shape[1] != sizes[rank]:
+        raise ValueError("gather_columns: rank %d holds %d columns, the partition of %d over %d ranks gives it %d"
+                         % (rank, local.shape[1], n_total, world, sizes[rank]))
     rows = local.shape[0]
     width = max(sizes)
     pad = torch.zeros((rows, width), dtype=local.dtype, device=local.device)
@@ -49,6 +52,25 @@ def gather_columns(local, n_total, dst=0):
     if rank != dst:
         return None
     return torch.cat([bufs[r][:, : sizes[r]] for r in range(world)], dim=1)
+
+
+def gather_rows(local, n_total, dst=0):
+    """Gather per-vector blocks along axis 0: local (n_local, ...) on every rank -> (n_total, ...) on `dst` (None
+    elsewhere).  Row blocks follow split_range (e.g. the (nR, nbx, nby) histogram counts)."""
+    import torch
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(), dist.get_rank()
+    sizes = split_sizes(n_total, world)
+    if local.shape[0] != sizes[rank]:
+        raise ValueError("gather_rows: rank %d holds %d rows, the partition of %d over %d ranks gives it %d"
+                         % (rank, local.shape[0], n_total, world, sizes[rank]))
+    pad = torch.zeros((max(sizes),) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    bufs = [torch.empty_like(pad) for _ in range(world)] if rank == dst else None
+    dist.gather(pad, bufs, dst=dst)
+    if rank != dst:
+        return None
+    return torch.cat([bufs[r][: sizes[r]] for r in range(world)], dim=0)
 
 
 def merge_lag_results(local, lags, world, dst=0):

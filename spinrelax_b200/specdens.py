@@ -324,23 +324,27 @@ class globalRotationalDiffusion_Axisymmetric(globalRotationalDiffusion_Base):
     def calc_Jomega_rigid(self, omega):
         return self.get_A_coefficients() * self.D_J / (np.power(self.D_J, 2.0) + np.power(omega, 2.0))
 
-    def a_moments(self):
-        """Per-residue weighted mean / covariance of A_J over the bins, computed once on the GPU."""
-        if getattr(self, "_amom", None) is None:
-            torch = _lib.require_cuda()
-            lib = _lib.load()
-            shared = getattr(self, "_shared_bins", False)
-            if shared:
-                A = np.ascontiguousarray(self.A_J[:, 0, :], dtype=np.float64)                    # (B, 3)
-            else:
-                A = np.ascontiguousarray(np.swapaxes(self.A_J, 0, 1), dtype=np.float64)          # (nR, B, 3)
-            W = np.ascontiguousarray(np.swapaxes(self.vecWeights, 0, 1), dtype=np.float64)      # (nR, B)
-            Ad, Wd = torch.from_numpy(A).cuda(), torch.from_numpy(W).cuda()
-            out = torch.empty((W.shape[0], 10), dtype=torch.float64, device=Ad.device)
-            _lib.check(lib.sr_relax_a_moments(Ad.data_ptr(), 0 if shared else 1, Wd.data_ptr(), W.shape[0], W.shape[1],
-                                              out.data_ptr(), _lib.current_stream_ptr()), "sr_relax_a_moments")
+    def a_moments(self, rows=None):
+        """Per-residue weighted mean / covariance of A_J over the bins, computed once on the GPU.  `rows` = (first, last)
+        computes (uncached) the moments of that block of residues on the current device: the multi-GPU grid."""
+        if rows is None and getattr(self, "_amom", None) is not None:
+            return self._amom
+        torch = _lib.require_cuda()
+        lib = _lib.load()
+        shared = getattr(self, "_shared_bins", False)
+        a, b = (0, self.vecWeights.shape[1]) if rows is None else rows
+        if shared:
+            A = np.ascontiguousarray(self.A_J[:, 0, :], dtype=np.float64)                    # (B, 3)
+        else:
+            A = np.ascontiguousarray(np.swapaxes(self.A_J[:, a:b], 0, 1), dtype=np.float64)  # (nR, B, 3)
+        W = np.ascontiguousarray(np.swapaxes(self.vecWeights[:, a:b], 0, 1), dtype=np.float64)   # (nR, B)
+        Ad, Wd = torch.from_numpy(A).cuda(), torch.from_numpy(W).cuda()
+        out = torch.empty((W.shape[0], 10), dtype=torch.float64, device=Ad.device)
+        _lib.check(lib.sr_relax_a_moments(Ad.data_ptr(), 0 if shared else 1, Wd.data_ptr(), W.shape[0], W.shape[1],
+                                          out.data_ptr(), _lib.current_stream_ptr()), "sr_relax_a_moments")
+        if rows is None:
             self._amom = out
-        return self._amom
+        return out
 
 
 # ---- batched GPU evaluation -----------------------------------------------------------------------
@@ -359,7 +363,7 @@ def _pack_models(models):
 
 
 def _gpu_relax(rotdif, models, omega, f_csa, f_dd, gammaA=-27.116e6, gammaB=267.513e6, time_fact=1e-12,
-               csa_per_residue=False, want="R", subset=None):
+               csa_per_residue=False, want="R", subset=None, rows=None):
     """omega (nField,5); f_csa (nField,nCSA) or (nField,nR).  Returns (nR,nField,nCSA,6), or J (nR,nField,5)
     for the isotropic `want='J'` path (evaluated through R-linearity is not possible, so J is computed with
     the GPU Lorentzian table)."""
@@ -382,7 +386,7 @@ def _gpu_relax(rotdif, models, omega, f_csa, f_dd, gammaA=-27.116e6, gammaB=267.
     t = lambda a, dt=torch.float64: torch.from_numpy(np.ascontiguousarray(a)).to(dev, dtype=dt)   # noqa: E731
     amom = None
     if not iso:
-        amom = rotdif.a_moments()
+        amom = rotdif.a_moments(rows)
         if subset is not None:
             amom = amom[torch.as_tensor(subset, device=dev, dtype=torch.long)].contiguous()
     D_J = (ctypes.c_double * 3)(*([rotdif.D, 0, 0] if iso else [float(x) for x in rotdif.D_J]))
@@ -403,8 +407,15 @@ def relax_grid(rotdif, Autocorrs, fields_mhz, csa_grid=None, nucleiA='15N', nucl
     omega = np.array([w.omega for w in ws])
     csa = np.atleast_1d(np.asarray(ws[0].gA.csa if csa_grid is None else csa_grid, dtype=float))
     f_csa = np.array([2.0 / 15.0 * csa ** 2.0 * (w.gA.gamma * w.B0) ** 2 for w in ws])
-    out = _gpu_relax(rotdif, models, omega, f_csa, ws[0].get_factor_DD(), ws[0].gA.gamma, ws[0].gB.gamma,
-                     ws[0].time_fact)
+    from . import multigpu
+    blocks = multigpu.plan(len(models), min_per_device=128)
+    if len(blocks) == 1:
+        out = _gpu_relax(rotdif, models, omega, f_csa, ws[0].get_factor_DD(), ws[0].gA.gamma, ws[0].gB.gamma,
+                         ws[0].time_fact)
+    else:       # residues are independent: every selected GPU evaluates a block of them (moments pass included)
+        out = np.concatenate(multigpu.run(blocks, lambda d, a, b: _gpu_relax(
+            rotdif, models[a:b], omega, f_csa, ws[0].get_factor_DD(), ws[0].gA.gamma, ws[0].gB.gamma, ws[0].time_fact,
+            rows=(a, b))), axis=0)
     iso = isinstance(rotdif, globalRotationalDiffusion_Isotropic)
     return {n: (out[..., i], None if iso else out[..., 3 + i]) for i, n in enumerate(("R1", "R2", "NOE"))}
 

@@ -67,12 +67,15 @@ def test_device_solve_marshals_arguments_as_the_header_declares(monkeypatch):
             return getattr(torch, k)
 
         @staticmethod
-        def device(_):
+        def device(*_):
             return torch.device("cpu")
 
     monkeypatch.setattr(_lib, "require_cuda", lambda: FakeTorch())
     monkeypatch.setattr(_lib, "load", lambda: FakeLib)
     monkeypatch.setattr(_lib, "current_stream_ptr", lambda: None)
+    from spinrelax_b200 import multigpu
+    monkeypatch.setattr(multigpu, "plan", lambda n, min_per_device=1: [(0, 0, n)])       # one device, all residues
+    monkeypatch.setattr(multigpu, "run", lambda blocks, fn: [fn(*b) for b in blocks])
     rng = np.random.default_rng(3)
     nR, L, nP = 4, 11, 5
     t, y, sg = np.arange(1.0, L + 1), rng.random((nR, L)), rng.random((nR, L)) + 0.1

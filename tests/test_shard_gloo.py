@@ -37,15 +37,26 @@ def _worker(rank, world, port, nR, nLags, out_dir):
         # frame-sharded histogram: all-reduce of integer counts
         h = torch.full((3, 4), rank + 1, dtype=torch.int64)
         shard.allreduce_sum_(h)
+        # vector-sharded histogram: per-vector (nbx, nby) count blocks gathered along axis 0 (uneven shares included)
+        hv = torch.arange(a, b, dtype=torch.int32)[:, None, None] * 100 + torch.arange(6, dtype=torch.int32).reshape(1, 3, 2)
+        hall = shard.gather_rows(hv, nR, dst=0)
+        # a block of the wrong width must be refused, not silently truncated / misplaced (uneven partitions)
+        bad = False
+        if nR % world:
+            try:
+                shard.gather_columns(torch.zeros((L, (b - a) + 1)), nR, dst=0)
+            except ValueError:
+                bad = True
         if rank == 0:
-            np.savez(os.path.join(out_dir, "r0.npz"), full=full.numpy(), merged=merged.numpy(), h=h.numpy())
+            np.savez(os.path.join(out_dir, "r0.npz"), full=full.numpy(), merged=merged.numpy(), h=h.numpy(), hall=hall.numpy(),
+                     refused=bad or not nR % world)
         else:
-            assert full is None and merged is None
+            assert full is None and merged is None and hall is None
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("nR,nLags", [(76, 100), (5, 3), (2, 1)])
+@pytest.mark.parametrize("nR,nLags", [(76, 100), (5, 3), (2, 1), (77, 10)])
 def test_gloo_world2(tmp_path, nR, nLags):
     world = 2
     mp.spawn(_worker, args=(world, _free_port(), nR, nLags, str(tmp_path)), nprocs=world, join=True)
@@ -55,6 +66,8 @@ def test_gloo_world2(tmp_path, nR, nLags):
     assert np.array_equal(r["full"], expect.astype(np.float32))
     assert np.array_equal(r["merged"][:, 0], np.arange(3, 3 + nLags))
     assert (r["h"] == 3).all()
+    assert np.array_equal(r["hall"], np.arange(nR)[:, None, None] * 100 + np.arange(6).reshape(1, 3, 2))
+    assert bool(r["refused"])
 
 
 def test_partition_properties():
