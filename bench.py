@@ -6,9 +6,16 @@
 
 One step = one pass of the hot path over the batch: K2 pack -> K1 lag sums -> Palmer finalize
 (-> K3 rotation + histogram).  `value` is timed with inputs resident in HBM, `e2e` goes through the
-public host-buffer call (pinned host input, H2D, kernels, D2H).  N > 1: one process per GPU (torchrun),
-every rank owns its own shard of bond vectors (weak scaling, no data-path collective; the (L, nR)
-result rows are gathered to rank 0 inside the timed region).
+public host-buffer call (pinned host input, H2D, kernels, D2H).
+
+N = 1: BASELINE config 2 (the configuration the metric is quoted on), plus -- outside the timed region, in the same JSON
+line under `secondary` -- the other BASELINE metrics: config 3 dq moments (run-all lag set and all windows), config 5
+fits and the R1/R2/NOE grid, each with its own roofline / CPU baseline and the clocks sampled while they ran.
+N > 1: one process per GPU (torchrun), BASELINE config 4: 1000 N-H + 1000 Calpha-Halpha vectors x 10^6 frames,
+sharded by bond vector over the ranks (strong scaling: the job is the same at every N > 1; no data-path collective,
+the (2L, nR) result columns and the per-vector histograms are gathered to rank 0 inside the timed region).  After the
+timed region every rank checks four of its vectors against the FFT oracle and the line carries the worst deviation;
+`secondary` then holds the two collective-terminated stages (pooled dq moments, frame-sharded histogram).
 """
 import argparse
 import json
@@ -30,11 +37,25 @@ METRIC = "ct_pairs_per_s"
 UNIT = "bond-vector*frame*lag pairs/s"
 
 
+C4_N_VEC = 2000        # BASELINE configs[3]: 1000 N-H + 1000 Calpha-Halpha
+
+
 def n_pairs(nR, nC, nF, L):
     return nR * nC * (L * nF - L * (L + 1) // 2)
 
 
 def workload_config(n_gpus):
+    if n_gpus > 1:
+        from spinrelax_b200 import shard
+        sizes = shard.split_sizes(C4_N_VEC, n_gpus)
+        return {"workload": "BASELINE config 4: %d bond vectors (1000 N-H + 1000 Calpha-Halpha) x 1e6 frames (%d chunks x %d), "
+                            "max lag %d, C(t) Palmer + PAF rotation + 72x36 vecHistogram, sharded by bond vector over %d GPUs"
+                            % (C4_N_VEC, N_CHUNK, N_FRAMES_PER_CHUNK, N_FRAMES_PER_CHUNK // 2, n_gpus),
+                "n_vectors": C4_N_VEC, "n_vectors_per_gpu": sizes, "n_chunks": N_CHUNK, "frames_per_chunk": N_FRAMES_PER_CHUNK,
+                "max_lag": N_FRAMES_PER_CHUNK // 2, "sharding": "bond vectors, contiguous balanced blocks (shard.split_range)",
+                "l2": "inputs (%.1f GB AoS per GPU) exceed the 126 MB L2; no flush needed" % (max(sizes) * 12e6 / 1e9),
+                "n1_workload": "bench.py --gpus 1 runs BASELINE config 2 (76 vectors); per-GPU work here is %d vectors" % max(sizes),
+                "pairs_per_step": n_pairs(C4_N_VEC, N_CHUNK, N_FRAMES_PER_CHUNK, N_FRAMES_PER_CHUNK // 2)}
     return {"workload": "BASELINE config 2: %d N-H vectors x 1e6 frames (%d chunks x %d), max lag %d, "
                         "C(t) Palmer + PAF rotation + 72x36 vecHistogram" % (N_VEC, N_CHUNK, N_FRAMES_PER_CHUNK,
                                                                              N_FRAMES_PER_CHUNK // 2),
@@ -48,6 +69,39 @@ def make_input(rank):
     from spinrelax_b200 import synth
     v = synth.nh_vectors(N_CHUNK * N_FRAMES_PER_CHUNK, N_VEC, seed=synth.BASE_SEED + 2 + 1000 * rank)
     return v.reshape(N_CHUNK, N_FRAMES_PER_CHUNK, N_VEC, 3)
+
+
+def make_input_c4_device(rank, world, dev):
+    """This rank's block of the config-4 vector set, built on the device: every vector is one of the 76 seeded
+    config-2 trajectories rolled along the frame axis of each chunk and turned by its own fixed rotation (same
+    autocorrelation, different data), so no rank ever holds more than its own share."""
+    import torch
+    from spinrelax_b200 import shard, synth
+    base = torch.from_numpy(make_input(0)).to(dev)                       # (nC, nF, 76, 3)
+    rng = np.random.default_rng(synth.BASE_SEED + 4040)
+    quat = rng.standard_normal((C4_N_VEC, 4))
+    quat /= np.linalg.norm(quat, axis=1, keepdims=True)
+    shift = rng.integers(0, N_FRAMES_PER_CHUNK, C4_N_VEC)
+    a, b = shard.split_range(C4_N_VEC, world, rank)
+    out = torch.empty((N_CHUNK, N_FRAMES_PER_CHUNK, b - a, 3), dtype=torch.float32, device=dev)
+    for j in range(a, b):
+        w, x, y, z = quat[j]
+        R = torch.tensor([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                          [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                          [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]], dtype=torch.float32, device=dev)
+        out[:, :, j - a] = torch.roll(base[:, :, j % N_VEC], int(shift[j]), dims=1) @ R.T
+    del base
+    return out
+
+
+def spot_check(step, v_host4, cols):
+    """After the timed region: C(t) of a few of this rank's vectors against the FFT oracle (float64, a different
+    algorithm), and every histogram must have counted each frame once.  Returns the worst relative deviation."""
+    from oracle import ct_oracle
+    S = ct_oracle.ct_lag_sums_fft(v_host4[:, :, cols])
+    oCt, _ = ct_oracle.ct_from_lag_sums(S, v_host4.shape[1], dtype=np.float64)
+    ours = step.Ct[:, cols].cpu().numpy().astype(np.float64)
+    return float(np.max(np.abs(ours - oCt) / np.abs(oCt)))
 
 
 class ClockSampler:
@@ -199,12 +253,19 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     lib = _lib.load()
 
-    v_host = torch.from_numpy(make_input(rank)).pin_memory()
-    nC, nF, nR = N_CHUNK, N_FRAMES_PER_CHUNK, N_VEC
+    nC, nF = N_CHUNK, N_FRAMES_PER_CHUNK
     L = nF // 2
-    v_dev = v_host.to(dev, non_blocking=True)
+    if world == 1:
+        v_host = torch.from_numpy(make_input(rank)).pin_memory()
+        nR = n_total = N_VEC
+        v_dev = v_host.to(dev, non_blocking=True)
+    else:
+        v_dev = make_input_c4_device(rank, world, dev)
+        nR, n_total = v_dev.shape[2], C4_N_VEC
+        v_host = torch.empty(v_dev.shape, dtype=torch.float32).pin_memory()
+        v_host.copy_(v_dev)
     torch.cuda.synchronize()
-    step = pipeline.CtHistStep(nC, nF, nR, q_rot=Q_PAF, device=dev, world=world, rank=rank)
+    step = pipeline.CtHistStep(nC, nF, nR, q_rot=Q_PAF, device=dev, world=world, rank=rank, n_total=n_total)
 
     def barrier():
         if world > 1:
@@ -252,14 +313,36 @@ def run_ours(args):
         dropin_s = time.perf_counter() - t0
         del v_page
 
-    t = torch.tensor([ms_total, e2e_s], dtype=torch.float64, device=dev)
+    # ---- after the timed regions: result check on every rank, worst deviation to rank 0 -------------------------------
+    step.run_device(v_dev)
+    torch.cuda.synchronize()
+    cols = sorted(set([0, nR // 3, (2 * nR) // 3, nR - 1]))
+    dev_ct = spot_check(step, v_np, cols)
+    hist_ok = 1.0
+    if step.has_hist:
+        _, _, h = step.run_device(v_dev)
+        hist_ok = float(np.all(h.reshape(nR, -1).sum(axis=1) == nC * nF))
+    t = torch.tensor([ms_total, e2e_s, dev_ct, -hist_ok], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, e2e_s = float(t[0]), float(t[1])
+    ms_total, e2e_s, dev_ct, hist_ok = float(t[0]), float(t[1]), float(t[2]), -float(t[3])
+    gathered_ok = None
+    if world > 1 and rank == 0:
+        # the gathered columns of this rank's own block must be the rank's own result, bit for bit
+        a0, b0 = 0, nR
+        gathered_ok = bool(torch.equal(step.gathered[:L, a0:b0], step.Ct) and step.gathered.shape == (2 * L, n_total)
+                           and step.gathered_hist.shape[0] == n_total)
+
+    secondary = None
+    try:
+        secondary = run_secondary(world, rank, local, dev)
+    except Exception as exc:                                   # the headline line must survive a secondary failure
+        secondary = {"error": "%s: %s" % (type(exc).__name__, exc)}
 
     if rank == 0:
-        pairs_gpu = n_pairs(nR, nC, nF, L)
-        value = pairs_gpu * world * args.steps / (ms_total * 1e-3)
+        pairs_gpu = n_pairs(nR, nC, nF, L)                    # rank 0 holds a largest block of the partition
+        pairs_job = n_pairs(n_total, nC, nF, L) if world > 1 else pairs_gpu
+        value = pairs_job * args.steps / (ms_total * 1e-3)
         pk = peaks()
         lag_ms = kt["ct_lag_kernel"]
         achieved = pairs_gpu * 7 / (lag_ms * 1e-3) / 1e12
@@ -277,13 +360,17 @@ def run_ours(args):
         cpu = cpu_baseline_single(v_np) if world == 1 else None
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32 products, f64 accumulation",
+                "scaling": "weak" if world == 1 else "strong", "vs_baseline": None, "dtype": "f32 products, f64 accumulation",
                 "data": "synthetic", "config": workload_config(world), "clocks": clocks,
-                "e2e": {"value": pairs_gpu * world * e2e_steps / e2e_s, "unit": UNIT,
+                "e2e": {"value": pairs_job * e2e_steps / e2e_s, "unit": UNIT,
                         "h2d_bytes_per_step": int(v_np.nbytes), "d2h_bytes_per_step": int(step.d2h_bytes()),
                         "steps": e2e_steps, "api": "spinrelax_b200.pipeline.CtHistStep.run_host: pinned NumPy in -> per-chunk H2D pipelined with "
                         "sr_pack_vectors_f32_chunks, sr_ct_lag_sums_chunks -> sr_ct_palmer_finalize, sr_sphere_hist (C ABI) -> D2H"},
-                "gpu_launches": step.launches_per_step() * args.steps, "roofline": roof, "cpu_baseline": cpu}
+                "gpu_launches": step.launches_per_step() * args.steps, "roofline": roof, "cpu_baseline": cpu,
+                "check": {"ct_max_rel_dev_vs_fft_oracle": dev_ct, "vectors_checked_per_rank": len(cols),
+                          "every_frame_binned_once": bool(hist_ok), "gathered_block_equals_local": gathered_ok,
+                          "when": "after the timed regions, every rank, max over ranks"},
+                "secondary": secondary}
         if dropin_s is not None:
             line["e2e_dropin"] = {"value": pairs_gpu / dropin_s, "unit": UNIT, "seconds": dropin_s,
                                   "api": "spinrelax_b200.ct.calculate_Ct_Palmer(vecs) on a pageable NumPy array -> "
@@ -291,6 +378,25 @@ def run_ours(args):
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_secondary(world, rank, local, dev):
+    """The other BASELINE metrics, measured right after the headline with their own clock samples (rank 0 reports).
+    N = 1: config 3 dq moments, config 5 fits and relaxation grid (bench_secondary.py).  N > 1: the two stages of the
+    path that end in a collective (bench_multi.py)."""
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    if world == 1:
+        import bench_secondary
+        lines = bench_secondary.bench_dq(False, emit=False) + bench_secondary.bench_fit_relax(False, emit=False)
+    else:
+        import bench_multi
+        lines = bench_multi.run(emit=False)
+    clocks = sampler.stop() if rank == 0 else None
+    if rank != 0:
+        return None
+    return {"clocks": clocks, "lines": lines}
 
 
 def main():

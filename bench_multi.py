@@ -20,18 +20,18 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 
-def main():
+def run(emit=True):
+    """Both stages on the already initialised process group (bench.py calls this after its own timed region);
+    returns the two JSON lines on rank 0, [] elsewhere."""
     import torch
     import torch.distributed as dist
     from spinrelax_b200 import _lib, hist, synth
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
+    lines = []
 
     def barrier():
         if world > 1:
@@ -81,7 +81,7 @@ def main():
     ref = torch.stack((outer[0, 0], outer[0, 1], outer[0, 2], outer[1, 1], outer[1, 2], outer[2, 2]))
     err = float(torch.max(torch.abs(got - ref) / torch.abs(ref)))
     if rank == 0:
-        print(json.dumps({"metric": "dq_pairs_per_s", "value": pairs / ms * 1e3, "unit": "frame*lag pairs/s", "n_gpus": world,
+        lines.append(({"metric": "dq_pairs_per_s", "value": pairs / ms * 1e3, "unit": "frame*lag pairs/s", "n_gpus": world,
                           "ms_per_step": ms, "scaling": "weak", "collective": "1 x NCCL all-reduce sum f64 (%d bytes)"
                           % (M.numel() * 8), "config": {"workload": "c3 all windows, one 1e6-frame replica per rank, pooled "
                           "moments (calculate-dq-distribution-multi semantics), 4 sub-chunks"}, "data": "synthetic",
@@ -108,12 +108,27 @@ def main():
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
     ok = bool((tot.sum(dim=(1, 2)) == F * world).all())
     if rank == 0:
-        print(json.dumps({"metric": "hist_samples_per_s", "value": F * nR * world / ms * 1e3, "unit": "vector*frame samples/s",
+        lines.append(({"metric": "hist_samples_per_s", "value": F * nR * world / ms * 1e3, "unit": "vector*frame samples/s",
                           "n_gpus": world, "ms_per_step": ms, "scaling": "weak",
                           "collective": "1 x NCCL all-reduce sum i32 (%d bytes)" % (acc.counts.numel() * 4),
                           "config": {"workload": "PAF rotation + 72x36 histogram, 76 vectors, 1e6 frames per rank"},
                           "data": "synthetic", "every_sample_counted_once": ok}))
     assert ok
+    if emit:
+        for l in lines:
+            print(json.dumps(l))
+    return lines
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    run(emit=True)
     if world > 1:
         dist.destroy_process_group()
 

@@ -33,7 +33,7 @@ def ev_ms(torch, fn, reps=3):
     return best
 
 
-def bench_dq(quick):
+def bench_dq(quick, emit=True):
     import torch
     from oracle import dq_oracle
     from spinrelax_b200 import _lib, dq, synth
@@ -51,8 +51,18 @@ def bench_dq(quick):
         ms = ev_ms(torch, lambda: _lib.check(lib.sr_dq_moments(qd.data_ptr(), N, ld.data_ptr(), len(lags), int(lags.min()), 4,
                                                                M.data_ptr(), None)))
         pairs = float(np.sum(N - lags))
+        # end to end like the CLI (calculate-dq-distribution.py --iso --aniso --num_chunk 4): H2D, the reduction over ALL lags
+        # of the list, the per-lag eigen-frames / rotated tensors, and the 20 Powell fits (iso, 4 chunk-iso, 3 aniso, 12
+        # chunk-aniso) that turn the curves into D
+        import contextlib
         t0 = time.perf_counter()
-        res = dq.dq_curves(q, lags[:100] if len(lags) > 100 else lags, 10.0, nchunk=4)      # e2e incl. H2D, eigh per lag
+        res = dq.dq_curves(q, lags, 10.0, nchunk=4)
+        t_curves = time.perf_counter() - t0
+        with contextlib.redirect_stdout(io.StringIO()):
+            taus = [dq.conduct_exponential_fit(res["dt"], res["iso"], 1.5, -0.5)]
+            taus += [dq.conduct_exponential_fit(res["dt"], res["chunk_iso"][i], 1.5, -0.5) for i in range(4)]
+            taus += [dq.conduct_exponential_fit(res["dt"], res["aniso2"][i], 0.5, 0.5) for i in range(3)]
+            taus += [dq.conduct_exponential_fit(res["dt"], res["chunk_aniso2"][i][j], 0.5, 0.5) for i in range(4) for j in range(3)]
         e2e_s = time.perf_counter() - t0
         # 40 FP64 flop per pair: 28 for the quaternion product + 12 for the six moments
         line = {"metric": "dq_pairs_per_s", "value": pairs / ms * 1e3, "unit": "frame*lag pairs/s", "n_gpus": 1,
@@ -62,7 +72,9 @@ def bench_dq(quick):
                              "unit": "TFLOP/s", "peak": 148 * 64 * 2 * 1.965e9 / 1e12,
                              "peak_source": "148 SM x 64 FP64 lanes x 2 x 1965 MHz (measured DFMA microbenchmark 34.2)",
                              "frac": pairs * 40 / ms * 1e-9 / (148 * 64 * 2 * 1.965e9 / 1e12)},
-                "e2e_first_100_lags_s": e2e_s}
+                "e2e": {"seconds": e2e_s, "curves_seconds": t_curves, "value": pairs / e2e_s, "unit": "frame*lag pairs/s",
+                        "what": "dq.dq_curves over the whole lag list (H2D, kernels, D2H, stacked eigh / frame quaternions) + 20 "
+                                "SciPy Powell fits, as the CLI runs them", "D_iso_from_fit": 0.5e12 / taus[0]}}
         out.append(line)
     # CPU baseline: the reference's per-lag body (obtain_self_dq + iso + tensor + chunks) via the oracle port
     t0 = time.perf_counter()
@@ -76,7 +88,9 @@ def bench_dq(quick):
            "sample": "oracle per-lag body (calculate-dq-distribution.py:560-625) for lags 1000, 50000, 100000 on the full trajectory"}
     for line in out:
         line["cpu_baseline"] = cpu
-        print(json.dumps(line))
+        if emit:
+            print(json.dumps(line))
+    return out
 
 
 def synth_curves(n_res, n_pts, seed):
@@ -94,7 +108,7 @@ def synth_curves(n_res, n_pts, seed):
     return t, Y, SG
 
 
-def bench_fit_relax(quick):
+def bench_fit_relax(quick, emit=True):
     import torch
     from oracle import ct_oracle, fit_oracle, sd_oracle
     from spinrelax_b200 import fitct, specdens as sd, synth
@@ -115,7 +129,8 @@ def bench_fit_relax(quick):
     for i in range(nref):
         fit_oracle.fit_ladder(t, Y[i], SG[i])
     cpu_fit = nref / (time.perf_counter() - t0)
-    print(json.dumps({"metric": "ct_fit_residues_per_s", "value": nR / fit_s, "unit": "residues/s (full 2-3-5-7-9 ladder, "
+    lines = []
+    lines.append(({"metric": "ct_fit_residues_per_s", "value": nR / fit_s, "unit": "residues/s (full 2-3-5-7-9 ladder, "
                       "500-point curves, host selection logic included)", "n_gpus": 1, "ms_per_step": fit_s * 1e3,
                       "config": {"workload": "c5 fits: %d residues x 500-point C(t)" % nR}, "dtype": "f64",
                       "kernel_ms": kern_ms, "kernel_only_residues_per_s": nR / (kern_ms * 1e-3),
@@ -148,7 +163,7 @@ def bench_fit_relax(quick):
     t0 = time.perf_counter()
     sd_oracle.relax_axisymmetric(600.133, 2.1e-5, 1.35, vec, wts[:nref], models[:nref], zeta=0.890023)
     cpu_rel = nref / (time.perf_counter() - t0)
-    print(json.dumps({"metric": "relax_evaluations_per_s", "value": n_eval / rel_s, "unit": "residue*field*CSA evaluations/s "
+    lines.append(({"metric": "relax_evaluations_per_s", "value": n_eval / rel_s, "unit": "residue*field*CSA evaluations/s "
                       "(each = R1, R2, NOE with mean and sigma over 2592 bin vectors; host packing + D2H included)",
                       "n_gpus": 1, "ms_per_step": rel_s * 1e3,
                       "config": {"workload": "c5 relaxation: %d residues x 5 fields x 64 CSA, 72x36 histogram" % nR},
@@ -156,9 +171,13 @@ def bench_fit_relax(quick):
                       "cpu_baseline": {"value": cpu_rel, "unit": "residue*field*CSA evaluations/s", "cores": 1, "kind": "port",
                                        "sample": "oracle relax_axisymmetric (spectral_densities.py:552-557,751-763,824-907) "
                                                  "on %d residues, 1 field, 1 CSA" % nref}}))
+    if emit:
+        for l in lines:
+            print(json.dumps(l))
+    return lines
 
 
-def bench_rtp():
+def bench_rtp(emit=True):
     """--vecDist spherical conversion on the config-2 stream (25.6M float32 vectors): HBM-bound, 24 B/vector."""
     import torch
     from oracle import ct_oracle
@@ -174,13 +193,16 @@ def bench_rtp():
     t0 = time.perf_counter()
     ct_oracle.xyz_to_rtp(sub)
     cpu = sub.shape[0] * nR / (time.perf_counter() - t0)
-    print(json.dumps({"metric": "rtp_vectors_per_s", "value": n / ms * 1e3, "unit": "vectors/s", "n_gpus": 1,
+    line = ({"metric": "rtp_vectors_per_s", "value": n / ms * 1e3, "unit": "vectors/s", "n_gpus": 1,
                       "ms_per_step": ms, "config": {"workload": "c2 stream: gm.xyz_to_rtp on (100000, 256, 3) float32"},
                       "dtype": "f32", "data": "synthetic",
                       "roofline": {"kernel": "xyz_to_rtp_vec4_kernel<float>", "bound": "hbm", "achieved": n * 24 / ms * 1e-6,
                                    "unit": "GB/s", "peak": peak, "frac": n * 24 / ms * 1e-6 / peak},
                       "cpu_baseline": {"value": cpu, "unit": "vectors/s", "cores": 1, "kind": "port",
-                                       "sample": "oracle xyz_to_rtp (general_maths.py:143-158) on 4000 frames x 256"}}))
+                                       "sample": "oracle xyz_to_rtp (general_maths.py:143-158) on 4000 frames x 256"}})
+    if emit:
+        print(json.dumps(line))
+    return line
 
 
 def main():

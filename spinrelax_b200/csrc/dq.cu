@@ -9,6 +9,8 @@
 // never need it; sr_dq_self applies it for callers that want the displacement quaternions themselves.
 #include "common.cuh"
 
+#include <mutex>
+
 namespace {
 
 constexpr int kDqThreads = 256;
@@ -17,6 +19,26 @@ constexpr int kDqTile = kDqThreads * kDqPerThread;   // frames per CTA (vec_mome
 constexpr int kDqLagTile = 16;                       // lags per CTA (dq_moments_kernel)
 constexpr int kDqFrameTile = 1024;                   // frames per CTA (dq_moments_kernel)
 constexpr int kDqU = 4;                              // q(t + delta) loads in flight per thread (x2: double buffered)
+constexpr int kDqSuper = 4;                          // frame tiles per super tile of the consecutive-lag kernel
+constexpr int kDqSuperFrames = kDqSuper * kDqFrameTile;
+
+// A (lag tile, super tile) is "interior" when the 16 lags of the tile are consecutive integers d0 .. d0 + 15, every
+// pair (t, t + delta) of the 4096-frame super tile exists for all of them, and for each lag the whole super tile
+// falls into one sub-chunk.  Interior super tiles are reduced by dq_moments_consec_kernel, everything else (edges of
+// the trajectory, sub-chunk boundaries, strided lag lists) by dq_moments_kernel; both evaluate this same predicate.
+__device__ __forceinline__ bool dq_super_interior(long long N, long long d0, int nInTile, long long lo, int nCh, int nRep,
+                                                  int replica) {
+  if (nInTile < kDqLagTile) return false;
+  const long long dmax = d0 + kDqLagTile - 1;
+  if (lo + kDqSuperFrames > N - dmax) return false;
+  for (int j = 0; j < kDqLagTile; ++j) {
+    const long long n = N - (d0 + j);
+    const long long nb = (n * nRep + nCh - 1) / nCh;
+    const long long off = (long long)replica * n;
+    if ((off + lo) / nb != (off + lo + kDqSuperFrames - 1) / nb) return false;
+  }
+  return true;
+}
 
 struct Vec3d { double x, y, z; };
 
@@ -38,7 +60,8 @@ __device__ __forceinline__ Vec3d dq_vector(const float4 a, const float4 b) {
 // FP64 instructions, 16 bytes of L1/L2 traffic.  grid.x = lagTile * tilesMax + frameTile.
 __global__ void __launch_bounds__(kDqThreads)
 dq_moments_kernel(const float4* __restrict__ q, long long N, const long long* __restrict__ lags, int nLags, int nCh,
-                  int tilesMax, int replica, int nRep, double* __restrict__ M) {
+                  int tilesMax, int replica, int nRep, const int* __restrict__ not_consecutive, double* __restrict__ M) {
+  const bool consecutive = not_consecutive != nullptr && *not_consecutive == 0;
   // left quaternions of the frame tile as four planes of doubles (w | x | y | z): a half-warp reads 16
   // consecutive doubles per plane (one wavefront, broadcast to the other half-warp); an array of double4
   // would cost 8 wavefronts per LDS.128 (32-byte lane stride) and saturate the shared-memory data pipe
@@ -54,6 +77,9 @@ dq_moments_kernel(const float4* __restrict__ q, long long N, const long long* __
   long long dmin = lags[lt * kDqLagTile];
   for (int j = 1; j < kDqLagTile && lt * kDqLagTile + j < nLags; ++j) dmin = min(dmin, lags[lt * kDqLagTile + j]);
   if (lo >= N - dmin) return;
+  // lag list made of consecutive integers: the interior of the (lag, frame) plane belongs to the other kernel
+  if (consecutive && dq_super_interior(N, dmin, min(kDqLagTile, nLags - lt * kDqLagTile),
+                                       (long long)(tile / kDqSuper) * kDqSuperFrames, nCh, nRep, replica)) return;
   for (int i = threadIdx.x; i < kDqFrameTile + 16 * kDqU; i += kDqThreads) {   // zero tail: see the pipeline below
     const long long t = lo + i;
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -116,6 +142,124 @@ dq_moments_kernel(const float4* __restrict__ q, long long N, const long long* __
       atomicAdd(m + 3, s3); atomicAdd(m + 4, s4); atomicAdd(m + 5, s5);
     }
   }
+}
+
+// Consecutive lags (the "all windows" lag list 1, 2, 3, ...): CTA = (tile of 16 consecutive lags d0 .. d0 + 15, super tile
+// of 4096 frames), interior tiles only (dq_super_interior).  Both operands come from shared memory as float64 planes
+// converted ONCE per CTA -- q(t) for the frame tile and q(t + d0 ...) for the 1024 + 16 frames the 16 lags reach -- so the
+// loop has no global load and no F2F: per pair 18 FP64 instructions and 3.5 shared-memory doubles.  Thread = (lag group
+// g of 4 lags, frame lane): in one step it takes the 2 consecutive frames 2 lane, 2 lane + 1 of a 128-frame slab against
+// its 4 lags, i.e. 8 pairs from 2 left and 5 right quaternions (LDS.128 on 16-byte lane strides: conflict free).  The 24
+// moment sums of a thread live in registers for the whole super tile; warp shuffle reduction, then one FP64 atomic per
+// (lag, moment) and warp.
+constexpr int kDqcPlaneA = kDqFrameTile;
+constexpr int kDqcPlaneB = kDqFrameTile + kDqLagTile;
+constexpr int kDqcSmemDoubles = 4 * kDqcPlaneA + 4 * kDqcPlaneB;
+
+__global__ void __launch_bounds__(kDqThreads, 2)
+dq_moments_consec_kernel(const float4* __restrict__ q, long long N, long long d_first, int nLags, int nCh, int superMax,
+                         int replica, int nRep, const int* __restrict__ not_consecutive, double* __restrict__ M) {
+  extern __shared__ __align__(16) double sh[];
+  if (*not_consecutive != 0) return;
+  double* const A = sh;
+  double* const B = sh + 4 * kDqcPlaneA;
+  const int lt = blockIdx.x / superMax;
+  const int st = blockIdx.x - lt * superMax;
+  const long long d0 = d_first + (long long)lt * kDqLagTile;
+  const long long lo0 = (long long)st * kDqSuperFrames;
+  if (!dq_super_interior(N, d0, min(kDqLagTile, nLags - lt * kDqLagTile), lo0, nCh, nRep, replica)) return;
+  const int g = threadIdx.x >> 6, lane = threadIdx.x & 63;          // lag group (4 lags), frame lane
+  double acc[4][6];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int m = 0; m < 6; ++m) acc[j][m] = 0.0;
+
+  for (int sub = 0; sub < kDqSuper; ++sub) {
+    const long long lo = lo0 + (long long)sub * kDqFrameTile;
+    __syncthreads();                                                // previous tile fully consumed
+    for (int i = threadIdx.x; i < kDqcPlaneB; i += kDqThreads) {
+      const float4 b = __ldg(q + lo + d0 + i);                      // interior: lo + d0 + i < N always
+      B[i] = (double)b.x; B[kDqcPlaneB + i] = (double)b.y; B[2 * kDqcPlaneB + i] = (double)b.z; B[3 * kDqcPlaneB + i] = (double)b.w;
+      if (i < kDqcPlaneA) {
+        const float4 a = __ldg(q + lo + i);
+        A[i] = (double)a.x; A[kDqcPlaneA + i] = (double)a.y; A[2 * kDqcPlaneA + i] = (double)a.z; A[3 * kDqcPlaneA + i] = (double)a.w;
+      }
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int slab = 0; slab < kDqFrameTile / 128; ++slab) {
+      const int f = slab * 128 + 2 * lane;                          // this thread's two frames f, f + 1
+      double aw[2], ax[2], ay[2], az[2];
+      {
+        const double2 w = *reinterpret_cast<const double2*>(A + f);
+        const double2 x = *reinterpret_cast<const double2*>(A + kDqcPlaneA + f);
+        const double2 y = *reinterpret_cast<const double2*>(A + 2 * kDqcPlaneA + f);
+        const double2 z = *reinterpret_cast<const double2*>(A + 3 * kDqcPlaneA + f);
+        aw[0] = w.x; aw[1] = w.y; ax[0] = x.x; ax[1] = x.y; ay[0] = y.x; ay[1] = y.y; az[0] = z.x; az[1] = z.y;
+      }
+      // right quaternions: frames f + 4 g .. f + 4 g + 4 relative to the B window (B[i] = q(lo + d0 + i))
+      double bw[5], bx[5], by[5], bz[5];
+      {
+        const int s = f + 4 * g;
+        const double* p = B + s;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const double* pc = p + c * kDqcPlaneB;
+          const double2 u0 = *reinterpret_cast<const double2*>(pc);
+          const double2 u1 = *reinterpret_cast<const double2*>(pc + 2);
+          const double u2 = pc[4];
+          double* dst = c == 0 ? bw : c == 1 ? bx : c == 2 ? by : bz;
+          dst[0] = u0.x; dst[1] = u0.y; dst[2] = u1.x; dst[3] = u1.y; dst[4] = u2;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const double w2 = bw[e + j], x2 = bx[e + j], y2 = by[e + j], z2 = bz[e + j];
+          // vector part of conj(a) * b, same expression tree as dq_moments_kernel
+          const double vx = fma(aw[e], x2, fma(-w2, ax[e], fma(az[e], y2, -(ay[e] * z2))));
+          const double vy = fma(aw[e], y2, fma(-w2, ay[e], fma(ax[e], z2, -(az[e] * x2))));
+          const double vz = fma(aw[e], z2, fma(-w2, az[e], fma(ay[e], x2, -(ax[e] * y2))));
+          acc[j][0] = fma(vx, vx, acc[j][0]); acc[j][1] = fma(vx, vy, acc[j][1]); acc[j][2] = fma(vx, vz, acc[j][2]);
+          acc[j][3] = fma(vy, vy, acc[j][3]); acc[j][4] = fma(vy, vz, acc[j][4]); acc[j][5] = fma(vz, vz, acc[j][5]);
+        }
+      }
+    }
+  }
+  // a warp holds one lag group: reduce its 24 sums and add them to the sub-chunk this super tile lies in
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const long long delta = d0 + 4 * g + j;
+    const long long n = N - delta;
+    const long long nb = (n * nRep + nCh - 1) / nCh;
+    const long long k = ((long long)replica * n + lo0) / nb;
+#pragma unroll
+    for (int m = 0; m < 6; ++m) {
+      const double v = sr_warp_sum(acc[j][m]);
+      if ((threadIdx.x & 31) == 0) atomicAdd(M + (((long long)lt * kDqLagTile + 4 * g + j) * nCh + k) * 6 + m, v);
+    }
+  }
+}
+
+// flag = 1 unless the lag list is d, d + 1, d + 2, ... (tested on the device: the call stays asynchronous)
+__global__ void dq_check_consecutive_kernel(const long long* __restrict__ lags, int nLags, long long first, int* flag) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nLags) return;
+  if (lags[i] != first + i) *flag = 1;
+}
+
+// one int of device scratch per call in flight: a small ring allocated once per device
+int* dq_flag_slot() {
+  static std::mutex mu;
+  static int* ring[64] = {nullptr};
+  static unsigned next[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lock(mu);
+  if (!ring[dev] && cudaMalloc(&ring[dev], 256 * sizeof(int)) != cudaSuccess) return nullptr;
+  return ring[dev] + (next[dev]++ & 255u);
 }
 
 __global__ void __launch_bounds__(256)
@@ -224,11 +368,31 @@ extern "C" int sr_dq_moments_pooled(const float* d_q, long long N, const long lo
   const long long blocks = tilesMax * lagTiles;
   SR_REQUIRE(blocks < (1LL << 31), "sr_dq_moments: %lld blocks exceed the grid limit; split the lag list", blocks);
   if (!accumulate) SR_CUDA(cudaMemsetAsync(d_M, 0, sizeof(double) * 6 * (size_t)nLags * nCh, (cudaStream_t)stream));
+  // a lag list of consecutive integers (all windows: 1, 2, 3, ...) takes the shared-memory kernel for the interior
+  // of the (lag, frame) plane; the list is tested on the device so that the call stays asynchronous
+  int* flag = nullptr;
+  if (nLags >= 2 * kDqLagTile) {
+    flag = dq_flag_slot();
+    SR_REQUIRE(flag != nullptr, "sr_dq_moments: cannot allocate device scratch");
+    SR_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), (cudaStream_t)stream));
+    dq_check_consecutive_kernel<<<(nLags + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_lags, nLags, min_lag, flag);
+  }
   const int smem = (kDqFrameTile + 16 * kDqU) * (int)sizeof(double4);
   SR_CUDA(cudaFuncSetAttribute(dq_moments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   dq_moments_kernel<<<(unsigned)blocks, kDqThreads, smem, (cudaStream_t)stream>>>((const float4*)d_q, N, d_lags, nLags,
-                                                                                 nCh, (int)tilesMax, replica, nReplicas, d_M);
+                                                                                 nCh, (int)tilesMax, replica, nReplicas,
+                                                                                 flag, d_M);
   SR_CUDA(cudaGetLastError());
+  if (flag) {
+    const long long superMax = (tilesMax + kDqSuper - 1) / kDqSuper;
+    const long long cblocks = superMax * lagTiles;
+    SR_REQUIRE(cblocks < (1LL << 31), "sr_dq_moments: %lld blocks exceed the grid limit; split the lag list", cblocks);
+    const int csmem = kDqcSmemDoubles * (int)sizeof(double);
+    SR_CUDA(cudaFuncSetAttribute(dq_moments_consec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, csmem));
+    dq_moments_consec_kernel<<<(unsigned)cblocks, kDqThreads, csmem, (cudaStream_t)stream>>>(
+        (const float4*)d_q, N, min_lag, nLags, nCh, (int)superMax, replica, nReplicas, flag, d_M);
+    SR_CUDA(cudaGetLastError());
+  }
   return SR_OK;
 }
 

@@ -136,6 +136,21 @@ def average_LegendreP1quat_chunk(ndat, vq, nchunk):
     return _iso_shipped(_vec_moment_sums(vq, nchunk))
 
 
+def _sym3_batch(m6):
+    """(..., 6) packed xx xy xz yy yz zz -> (..., 3, 3)."""
+    m6 = np.asarray(m6)
+    idx = np.array([[0, 1, 2], [1, 3, 4], [2, 4, 5]])
+    return m6[..., idx]
+
+
+def _rotated_batch(M, qframe):
+    """_rotated for a stack of tensors (..., 3, 3) and one frame quaternion."""
+    if qs.nearly_identity(qframe):
+        return M
+    R = qs.rotation_matrix(qframe)
+    return R @ M @ R.T
+
+
 def _rotated(M33, qframe):
     if qs.nearly_identity(qframe):
         return M33
@@ -182,42 +197,47 @@ def dq_curves(q, lags, ddt, nchunk=0, do_aniso=True):
     if nchunk > 1:
         out["chunk_iso"] = _iso_shipped(M).T.copy()
         out["chunk_aniso2"] = np.zeros((nchunk, 3, nl))
+    # everything below is O(#lags) host arithmetic of the reference's loop body (:566-625), evaluated for the whole lag
+    # list at once: stacked 3x3 eigen-decompositions, frame quaternions and rotations
     q_frame = IDENTITY
-    first = True
-    for k in range(nl):
-        moi = _sym3(full[k]) / n[k]
-        out["moi"][k] = moi
-        if do_aniso:
-            eigval, eigvec = np.linalg.eigh(moi)
-            axes = eigvec.T
-            q_rot = qs.quat_frame_transform_min(axes)
-            if first:
-                first = False
-                q_frame = q_rot
-            moiR = _rotated(moi, q_frame)
-            out["aniso1"][:, k] = 1 - 2 * eigval
-            out["aniso2"][:, k] = 1 - 2 * np.diag(moiR)
-            out["qrot"][:, k] = q_rot
-            out["moi_axes"][k] = axes
-            out["moiR"][k] = moiR
-        else:
-            out["moiR"][k] = moi
-        if nchunk > 1:
-            for c in range(nchunk):
-                t2 = _rotated(_sym3(M[k, c]) / counts[k, c], q_frame)
-                out["chunk_aniso2"][c, :, k] = 1 - 2 * np.diag(t2)
+    moi_all = _sym3_batch(full) / np.asarray(n, dtype=float)[:, None, None]
+    out["moi"][:] = moi_all
+    if do_aniso and nl:
+        eigval, eigvec = np.linalg.eigh(moi_all)
+        axes = np.swapaxes(eigvec, 1, 2)
+        q_rot = qs.quat_frame_transform_min_batch(axes)
+        q_frame = q_rot[0]                         # the frame of the first window is kept for all windows (:569-572)
+        moiR = _rotated_batch(moi_all, q_frame)
+        out["aniso1"][:] = (1 - 2 * eigval).T
+        out["aniso2"][:] = (1 - 2 * np.diagonal(moiR, axis1=1, axis2=2)).T
+        out["qrot"][:] = q_rot.T
+        out["moi_axes"][:] = axes
+        out["moiR"][:] = moiR
+    else:
+        out["moiR"][:] = moi_all
+    if nchunk > 1:
+        with np.errstate(invalid="ignore", divide="ignore"):
+            t2 = _rotated_batch(_sym3_batch(M) / counts[:, :, None, None], q_frame)          # (nl, nCh, 3, 3)
+        out["chunk_aniso2"][:] = np.transpose(1 - 2 * np.diagonal(t2, axis1=2, axis2=3), (1, 2, 0))
     out["q_frame"] = np.array(q_frame, dtype=float)
     return out
 
 
 # ---- fits and derived quantities (host, SciPy as in the reference) ------------------------------------
 def powell_expdecay(pos, *args):
+    """Mean squared deviation of C0 exp(-x/A) + C1 from y (calculate-dq-distribution.py:199-203 sums it point by point
+    in a Python loop).  Evaluated as array operations with the terms added left to right (np.add.accumulate is the
+    sequential sum, not NumPy's pairwise one), so the value is the loop's up to the last-bit difference between
+    libm's and NumPy's exp -- with 1e5 lag windows and ~100 objective calls per curve the loop would dominate the
+    whole stage."""
     x, y, C0, C1 = args
     A = float(np.ravel(pos)[0])
-    chi2 = 0.0
-    for i in range(len(x)):
-        chi2 += (C0 * math.exp(-x[i] / A) + C1 - y[i]) ** 2
-    return chi2 / len(x)
+    x, y = np.asarray(x, dtype=float), np.asarray(y, dtype=float)
+    if x.size == 0:
+        return 0.0 / len(x)
+    with np.errstate(over="ignore", divide="ignore", invalid="ignore"):
+        term = np.square(C0 * np.exp(-x / A) + C1 - y)
+    return float(np.add.accumulate(term)[-1]) / len(x)
 
 
 def obtain_exponential_guess(x, y, C1):

@@ -120,6 +120,41 @@ def quat_frame_transform_min(axes):
     return _qmult(q2, q1)
 
 
+# ---- the same algebra over a stack of frames: one call for a whole lag list (calculate-dq-distribution.py:554-650
+# evaluates it once per lag; with 1e5 lag windows a Python loop costs more than the GPU reduction it follows) ------
+def _qmult_batch(a, b):
+    w1, x1, y1, z1 = (a[..., i] for i in range(4))
+    w2, x2, y2, z2 = (b[..., i] for i in range(4))
+    return np.stack((w1 * w2 - x1 * x2 - y1 * y2 - z1 * z2, w1 * x2 + x1 * w2 + y1 * z2 - z1 * y2,
+                     w1 * y2 + y1 * w2 + z1 * x2 - x1 * z2, w1 * z2 + z1 * w2 + x1 * y2 - y1 * x2), axis=-1)
+
+
+def _quat_v1v2_batch(v1, v2):
+    """quat_v1v2 for v1 (n, 3) against one fixed unit vector v2: same operations element by element."""
+    v2 = np.asarray(v2, dtype=float)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        th = np.arccos(v1[:, 0] * v2[0] + v1[:, 1] * v2[1] + v1[:, 2] * v2[2])
+        ax = np.stack((v1[:, 1] * v2[2] - v1[:, 2] * v2[1], v1[:, 2] * v2[0] - v1[:, 0] * v2[2],
+                       v1[:, 0] * v2[1] - v1[:, 1] * v2[0]), axis=1)
+        dead = np.all(np.isnan(ax), axis=1)
+        ax = ax / np.sqrt(ax[:, 0] * ax[:, 0] + ax[:, 1] * ax[:, 1] + ax[:, 2] * ax[:, 2])[:, None]
+        out = np.concatenate((np.cos(th / 2.0)[:, None], ax * np.sin(th / 2.0)[:, None]), axis=1)
+    out[dead] = (1.0, 0.0, 0.0, 0.0)
+    return out
+
+
+def quat_frame_transform_min_batch(axes):
+    """quat_frame_transform_min for axes (n, 3, 3) (rows = the three axes of every frame): (n, 4)."""
+    axes = np.asarray(axes, dtype=float)
+    a, b = _quat_v1v2_batch(axes[:, 2], (0, 0, 1)), _quat_v1v2_batch(axes[:, 2], (0, 0, -1))
+    q1 = np.where((a[:, 0] > b[:, 0])[:, None], a, b)
+    v = np.concatenate((np.zeros((len(axes), 1)), axes[:, 0]), axis=1)
+    x_rot = _qmult_batch(q1, _qmult_batch(v, q1 * np.array([1.0, -1.0, -1.0, -1.0])))[:, 1:]
+    a, b = _quat_v1v2_batch(x_rot, (1, 0, 0)), _quat_v1v2_batch(x_rot, (-1, 0, 0))
+    q2 = np.where((a[:, 0] > b[:, 0])[:, None], a, b)
+    return _qmult_batch(q2, q1)
+
+
 def nearly_identity(q, rtol=1e-5, atol=1e-8):
     """transforms3d.quaternions.nearly_equivalent(q, (1,0,0,0)) as used at calculate-dq-distribution.py:124."""
     q = np.asarray(q, dtype=float)

@@ -66,6 +66,29 @@ def test_dq_ragged(N, lags, nch):
             assert np.allclose(dq._sym3(M[k, c]), np.einsum("ti,tj->ij", blk, blk), rtol=1e-11, atol=1e-18)
 
 
+@pytest.mark.parametrize("N,first,nl,nch,nrep", [(60000, 1, 200, 4, 1), (40000, 37, 131, 3, 1), (30000, 1, 96, 4, 3),
+                                                 (9000, 5, 64, 1, 1)])
+def test_dq_consecutive_lags_take_the_shared_memory_kernel(N, first, nl, nch, nrep):
+    """A lag list of consecutive integers ("all windows") is reduced by dq_moments_consec_kernel in the interior of
+    the (lag, frame) plane and by the generic kernel on the edges and sub-chunk boundaries: every (lag, sub-chunk)
+    block must equal the NumPy reduction, and the sums must equal those of the generic kernel alone (same lags given
+    in a permuted order, which is not a consecutive list)."""
+    from spinrelax_b200 import dq, synth
+    q = np.stack([synth.quaternion_walk(N, seed=100 * N + r) for r in range(nrep)])
+    lags = np.arange(first, first + nl)
+    M, n, counts = dq.dq_moment_sums(q if nrep > 1 else q[0], lags, nch)
+    perm = np.random.default_rng(1).permutation(nl)
+    Mg, _, _ = dq.dq_moment_sums(q if nrep > 1 else q[0], lags[perm], nch)
+    assert np.allclose(M[perm], Mg, rtol=1e-12, atol=1e-22)
+    for k in (0, 1, nl // 2, nl - 1):
+        vo = dq_oracle.pooled_vectors(q, int(lags[k]))
+        assert counts[k].sum() == len(vo) == n[k]
+        nb = -(-len(vo) // nch)
+        for c in range(nch):
+            blk = vo[nb * c: min(len(vo), nb * (c + 1))]
+            assert np.allclose(dq._sym3(M[k, c]), np.einsum("ti,tj->ij", blk, blk), rtol=1e-11, atol=1e-18), (k, c)
+
+
 def test_dq_curves_and_D_vs_oracle():
     """Anisotropic walk: curves to 1e-12, then the same SciPy Powell gives tau and D to 1e-6; q_rot up to sign."""
     from spinrelax_b200 import dq, synth
