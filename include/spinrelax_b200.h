@@ -179,6 +179,13 @@ int sr_dq_moments(const float* d_q, long long N, const long long* d_lags, int nL
 int sr_dq_moments_pooled(const float* d_q, long long N, const long long* d_lags, int nLags, long long min_lag, int nCh,
                          int replica, int nReplicas, int accumulate, double* d_M, void* stream);
 
+/* Objective of the 1-parameter Powell fits of the decay curves (powell_expdecay, calculate-dq-distribution.py:199-203):
+ * *d_out = mean_i (C0 exp(-x_i / A) + C1 - y_i)^2 for a curve (d_x, d_y, n doubles) resident on the device.  d_work:
+ * at least 129 doubles, zero-initialised once by the caller and reusable for every further evaluation on that stream.
+ * SciPy's fmin_powell stays on the host (:205) and calls this once per trial tau. */
+int sr_expdecay_chi2(const double* d_x, const double* d_y, long long n, double C0, double C1, double A, double* d_work,
+                     int work_doubles, double* d_out, void* stream);
+
 /* obtain_self_dq(q, delta): d_out (N-delta, 4) float64, imaged so that w >= 0 (quat_reduce_simd). */
 int sr_dq_self(const float* d_q, long long N, long long delta, double* d_out, void* stream);
 

@@ -50,6 +50,7 @@ def _declare(lib):
         "sr_dq_moments": (i, [vp, ll, vp, i, ll, i, vp, vp]),
         "sr_dq_moments_pooled": (i, [vp, ll, vp, i, ll, i, i, i, i, vp, vp]),
         "sr_dq_self": (i, [vp, ll, ll, vp, vp]),
+        "sr_expdecay_chi2": (i, [vp, vp, ll, _c.c_double, _c.c_double, _c.c_double, vp, i, vp, vp]),
         "sr_dq_hist3d": (i, [vp, ll, ll, vp, i, vp, vp, i, vp, vp]),
         "sr_vec_second_moments": (i, [vp, ll, i, vp, vp]),
         "sr_sphere_hist": (i, [vp, ll, i, dp, i, i, vp, _c.c_double, _c.c_double, vp, vp, i, vp, vp]),

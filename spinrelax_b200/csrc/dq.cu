@@ -9,6 +9,7 @@
 // never need it; sr_dq_self applies it for callers that want the displacement quaternions themselves.
 #include "common.cuh"
 
+#include <algorithm>
 #include <mutex>
 
 namespace {
@@ -24,20 +25,14 @@ constexpr int kDqSuperFrames = kDqSuper * kDqFrameTile;
 
 // A (lag tile, super tile) is "interior" when the 16 lags of the tile are consecutive integers d0 .. d0 + 15, every
 // pair (t, t + delta) of the 4096-frame super tile exists for all of them, and for each lag the whole super tile
-// falls into one sub-chunk.  Interior super tiles are reduced by dq_moments_consec_kernel, everything else (edges of
-// the trajectory, sub-chunk boundaries, strided lag lists) by dq_moments_kernel; both evaluate this same predicate.
-__device__ __forceinline__ bool dq_super_interior(long long N, long long d0, int nInTile, long long lo, int nCh, int nRep,
-                                                  int replica) {
-  if (nInTile < kDqLagTile) return false;
-  const long long dmax = d0 + kDqLagTile - 1;
-  if (lo + kDqSuperFrames > N - dmax) return false;
-  for (int j = 0; j < kDqLagTile; ++j) {
-    const long long n = N - (d0 + j);
-    const long long nb = (n * nRep + nCh - 1) / nCh;
-    const long long off = (long long)replica * n;
-    if ((off + lo) / nb != (off + lo + kDqSuperFrames - 1) / nb) return false;
-  }
-  return true;
+// falls into one sub-chunk.  dq_moments_consec_kernel reduces interior super tiles with its shared-memory fast path
+// and everything else (edges of the trajectory, sub-chunk boundaries) with the generic tile routine.
+__device__ __forceinline__ bool dq_lag_interior(long long N, long long delta, long long lo, int nCh, int nRep, int replica) {
+  const long long n = N - delta;
+  if (lo + kDqSuperFrames > n) return false;
+  const long long nb = (n * nRep + nCh - 1) / nCh;
+  const long long pos = (long long)replica * n + lo;
+  return pos / nb == (pos + kDqSuperFrames - 1) / nb;
 }
 
 struct Vec3d { double x, y, z; };
@@ -58,17 +53,12 @@ __device__ __forceinline__ Vec3d dq_vector(const float4 a, const float4 b) {
 // thread (lag j = tid >> 4, frame lane = tid & 15) streams q(t + delta_j) as coalesced float4 (consecutive
 // lags hit the same L1 lines) and keeps its six second-moment sums in registers.  Per pair: 4 F2F + 18
 // FP64 instructions, 16 bytes of L1/L2 traffic.  grid.x = lagTile * tilesMax + frameTile.
-__global__ void __launch_bounds__(kDqThreads)
-dq_moments_kernel(const float4* __restrict__ q, long long N, const long long* __restrict__ lags, int nLags, int nCh,
-                  int tilesMax, int replica, int nRep, const int* __restrict__ not_consecutive, double* __restrict__ M) {
-  const bool consecutive = not_consecutive != nullptr && *not_consecutive == 0;
+__device__ void dq_tile_generic(const float4* __restrict__ q, long long N, const long long* __restrict__ lags, int nLags,
+                                int nCh, int lt, int tile, int replica, int nRep, double* __restrict__ M, double* sh_a) {
   // left quaternions of the frame tile as four planes of doubles (w | x | y | z): a half-warp reads 16
   // consecutive doubles per plane (one wavefront, broadcast to the other half-warp); an array of double4
   // would cost 8 wavefronts per LDS.128 (32-byte lane stride) and saturate the shared-memory data pipe
-  extern __shared__ __align__(16) double sh_a[];
   constexpr int kPlane = kDqFrameTile + 16 * kDqU;
-  const int lt = blockIdx.x / tilesMax;
-  const int tile = blockIdx.x - lt * tilesMax;
   const long long lo = (long long)tile * kDqFrameTile;
   const int jl = threadIdx.x >> 4, fl = threadIdx.x & 15;
   const int li = lt * kDqLagTile + jl;
@@ -77,9 +67,6 @@ dq_moments_kernel(const float4* __restrict__ q, long long N, const long long* __
   long long dmin = lags[lt * kDqLagTile];
   for (int j = 1; j < kDqLagTile && lt * kDqLagTile + j < nLags; ++j) dmin = min(dmin, lags[lt * kDqLagTile + j]);
   if (lo >= N - dmin) return;
-  // lag list made of consecutive integers: the interior of the (lag, frame) plane belongs to the other kernel
-  if (consecutive && dq_super_interior(N, dmin, min(kDqLagTile, nLags - lt * kDqLagTile),
-                                       (long long)(tile / kDqSuper) * kDqSuperFrames, nCh, nRep, replica)) return;
   for (int i = threadIdx.x; i < kDqFrameTile + 16 * kDqU; i += kDqThreads) {   // zero tail: see the pipeline below
     const long long t = lo + i;
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -144,6 +131,14 @@ dq_moments_kernel(const float4* __restrict__ q, long long N, const long long* __
   }
 }
 
+__global__ void __launch_bounds__(kDqThreads)
+dq_moments_kernel(const float4* __restrict__ q, long long N, const long long* __restrict__ lags, int nLags, int nCh,
+                  int tilesMax, int replica, int nRep, double* __restrict__ M) {
+  extern __shared__ __align__(16) double sh_a[];
+  const int lt = blockIdx.x / tilesMax;
+  dq_tile_generic(q, N, lags, nLags, nCh, lt, blockIdx.x - lt * tilesMax, replica, nRep, M, sh_a);
+}
+
 // Consecutive lags (the "all windows" lag list 1, 2, 3, ...): CTA = (tile of 16 consecutive lags d0 .. d0 + 15, super tile
 // of 4096 frames), interior tiles only (dq_super_interior).  Both operands come from shared memory as float64 planes
 // converted ONCE per CTA -- q(t) for the frame tile and q(t + d0 ...) for the 1024 + 16 frames the 16 lags reach -- so the
@@ -155,19 +150,31 @@ dq_moments_kernel(const float4* __restrict__ q, long long N, const long long* __
 constexpr int kDqcPlaneA = kDqFrameTile;
 constexpr int kDqcPlaneB = kDqFrameTile + kDqLagTile;
 constexpr int kDqcSmemDoubles = 4 * kDqcPlaneA + 4 * kDqcPlaneB;
+static_assert(kDqcSmemDoubles >= 4 * (kDqFrameTile + 16 * kDqU), "the generic tile routine borrows this buffer");
 
 __global__ void __launch_bounds__(kDqThreads, 2)
-dq_moments_consec_kernel(const float4* __restrict__ q, long long N, long long d_first, int nLags, int nCh, int superMax,
-                         int replica, int nRep, const int* __restrict__ not_consecutive, double* __restrict__ M) {
+dq_moments_consec_kernel(const float4* __restrict__ q, long long N, const long long* __restrict__ lags, long long d_first,
+                         int nLags, int nCh, int superMax, int replica, int nRep, double* __restrict__ M) {
   extern __shared__ __align__(16) double sh[];
-  if (*not_consecutive != 0) return;
   double* const A = sh;
   double* const B = sh + 4 * kDqcPlaneA;
   const int lt = blockIdx.x / superMax;
   const int st = blockIdx.x - lt * superMax;
   const long long d0 = d_first + (long long)lt * kDqLagTile;
   const long long lo0 = (long long)st * kDqSuperFrames;
-  if (!dq_super_interior(N, d0, min(kDqLagTile, nLags - lt * kDqLagTile), lo0, nCh, nRep, replica)) return;
+  if (lo0 >= N - d0) return;                                         // no pair at all in this super tile
+  // interior test: one lag per thread (two 64-bit divisions each), combined over the CTA
+  int ok = 1;
+  if (threadIdx.x < kDqLagTile)
+    ok = (lt * kDqLagTile + (int)threadIdx.x < nLags) && dq_lag_interior(N, d0 + threadIdx.x, lo0, nCh, nRep, replica);
+  if (!__syncthreads_and(ok)) {
+    // edge of the trajectory, sub-chunk boundary or ragged last lag tile: the generic routine, tile by tile
+    for (int sub = 0; sub < kDqSuper; ++sub) {
+      dq_tile_generic(q, N, lags, nLags, nCh, lt, st * kDqSuper + sub, replica, nRep, M, sh);
+      __syncthreads();
+    }
+    return;
+  }
   const int g = threadIdx.x >> 6, lane = threadIdx.x & 63;          // lag group (4 lags), frame lane
   double acc[4][6];
 #pragma unroll
@@ -243,7 +250,7 @@ dq_moments_consec_kernel(const float4* __restrict__ q, long long N, long long d_
   }
 }
 
-// flag = 1 unless the lag list is d, d + 1, d + 2, ... (tested on the device: the call stays asynchronous)
+// flag = 1 unless the lag list is d, d + 1, d + 2, ...
 __global__ void dq_check_consecutive_kernel(const long long* __restrict__ lags, int nLags, long long first, int* flag) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nLags) return;
@@ -354,7 +361,59 @@ vec_moments_kernel(const double* __restrict__ v, long long n, int nCh, double* _
   }
 }
 
+// Objective of the reference's 1-parameter Powell fits (powell_expdecay, calculate-dq-distribution.py:199-203):
+// mean_i (C0 exp(-x_i / A) + C1 - y_i)^2 over a decay curve that stays on the device between the ~100 evaluations of
+// a fit.  Fixed-shape two-level reduction (every CTA sums a contiguous slice in a fixed order, the last CTA to finish
+// adds the partial sums in index order), so the value does not depend on scheduling.
+constexpr int kChiThreads = 256;
+constexpr int kChiBlocks = 128;
+
+__global__ void __launch_bounds__(kChiThreads)
+expdecay_chi2_kernel(const double* __restrict__ x, const double* __restrict__ y, long long n, double C0, double C1, double A,
+                     double* __restrict__ work, double* __restrict__ out) {
+  __shared__ double red[kChiThreads / 32];
+  __shared__ bool last;
+  const long long per = (n + gridDim.x - 1) / gridDim.x;
+  const long long a = per * blockIdx.x, b = min(n, a + per);
+  double s = 0.0;
+  for (long long i = a + threadIdx.x; i < b; i += kChiThreads) {
+    const double d = C0 * exp(-x[i] / A) + C1 - y[i];
+    s = fma(d, d, s);
+  }
+  s = sr_warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < kChiThreads / 32; ++w) t += red[w];
+    work[1 + blockIdx.x] = t;
+    __threadfence();
+    const unsigned ticket = atomicAdd(reinterpret_cast<unsigned int*>(work), 1u);
+    last = (ticket == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    double t = 0.0;
+    for (unsigned i = 0; i < gridDim.x; ++i) t += reinterpret_cast<volatile double*>(work)[1 + i];
+    *out = t / (double)n;
+    *reinterpret_cast<unsigned int*>(work) = 0u;          // ready for the next evaluation
+  }
+}
+
 }  // namespace
+
+extern "C" int sr_expdecay_chi2(const double* d_x, const double* d_y, long long n, double C0, double C1, double A,
+                                double* d_work, int work_doubles, double* d_out, void* stream) {
+  SR_REQUIRE(d_x && d_y && d_work && d_out, "sr_expdecay_chi2: null pointer");
+  SR_REQUIRE(n >= 1, "sr_expdecay_chi2: empty curve");
+  SR_REQUIRE(work_doubles >= kChiBlocks + 1, "sr_expdecay_chi2: workspace of %d doubles, need %d (zero-initialised)", work_doubles,
+             kChiBlocks + 1);
+  const int blocks = (int)std::min<long long>(kChiBlocks, (n + kChiThreads - 1) / kChiThreads);
+  expdecay_chi2_kernel<<<blocks, kChiThreads, 0, (cudaStream_t)stream>>>(d_x, d_y, n, C0, C1, A, d_work, d_out);
+  SR_CUDA(cudaGetLastError());
+  return SR_OK;
+}
 
 extern "C" int sr_dq_moments_pooled(const float* d_q, long long N, const long long* d_lags, int nLags, long long min_lag,
                                     int nCh, int replica, int nReplicas, int accumulate, double* d_M, void* stream) {
@@ -370,29 +429,32 @@ extern "C" int sr_dq_moments_pooled(const float* d_q, long long N, const long lo
   if (!accumulate) SR_CUDA(cudaMemsetAsync(d_M, 0, sizeof(double) * 6 * (size_t)nLags * nCh, (cudaStream_t)stream));
   // a lag list of consecutive integers (all windows: 1, 2, 3, ...) takes the shared-memory kernel for the interior
   // of the (lag, frame) plane; the list is tested on the device so that the call stays asynchronous
-  int* flag = nullptr;
+  // A lag list of consecutive integers (all windows: 1, 2, 3, ...) takes the shared-memory kernel.  The list lives on
+  // the device, so it is tested there and the one-word verdict is read back (the only synchronisation of this call:
+  // a few microseconds next to a reduction that runs for milliseconds).
+  int not_consecutive = 1;
   if (nLags >= 2 * kDqLagTile) {
-    flag = dq_flag_slot();
+    int* flag = dq_flag_slot();
     SR_REQUIRE(flag != nullptr, "sr_dq_moments: cannot allocate device scratch");
     SR_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), (cudaStream_t)stream));
     dq_check_consecutive_kernel<<<(nLags + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_lags, nLags, min_lag, flag);
+    SR_CUDA(cudaMemcpyAsync(&not_consecutive, flag, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    SR_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
   }
-  const int smem = (kDqFrameTile + 16 * kDqU) * (int)sizeof(double4);
-  SR_CUDA(cudaFuncSetAttribute(dq_moments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  dq_moments_kernel<<<(unsigned)blocks, kDqThreads, smem, (cudaStream_t)stream>>>((const float4*)d_q, N, d_lags, nLags,
-                                                                                 nCh, (int)tilesMax, replica, nReplicas,
-                                                                                 flag, d_M);
-  SR_CUDA(cudaGetLastError());
-  if (flag) {
+  if (not_consecutive) {
+    const int smem = (kDqFrameTile + 16 * kDqU) * (int)sizeof(double4);
+    SR_CUDA(cudaFuncSetAttribute(dq_moments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    dq_moments_kernel<<<(unsigned)blocks, kDqThreads, smem, (cudaStream_t)stream>>>((const float4*)d_q, N, d_lags, nLags,
+                                                                                   nCh, (int)tilesMax, replica, nReplicas, d_M);
+  } else {
     const long long superMax = (tilesMax + kDqSuper - 1) / kDqSuper;
     const long long cblocks = superMax * lagTiles;
-    SR_REQUIRE(cblocks < (1LL << 31), "sr_dq_moments: %lld blocks exceed the grid limit; split the lag list", cblocks);
     const int csmem = kDqcSmemDoubles * (int)sizeof(double);
     SR_CUDA(cudaFuncSetAttribute(dq_moments_consec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, csmem));
     dq_moments_consec_kernel<<<(unsigned)cblocks, kDqThreads, csmem, (cudaStream_t)stream>>>(
-        (const float4*)d_q, N, min_lag, nLags, nCh, (int)superMax, replica, nReplicas, flag, d_M);
-    SR_CUDA(cudaGetLastError());
+        (const float4*)d_q, N, d_lags, min_lag, nLags, nCh, (int)superMax, replica, nReplicas, d_M);
   }
+  SR_CUDA(cudaGetLastError());
   return SR_OK;
 }
 

@@ -32,8 +32,32 @@ struct FitShared {
   srtrf::Core<N> core;
   double red[2][kFitWarps][N + 2];
   double qtf[N];
+  double W[N * N];          // working copy of R for the Jacobi SVD (column major)
   int flag;
 };
+
+// SVD of core.R by warp 0 (all 32 lanes call this); results in core.s, core.V, core.suf, core.full_rank
+template <int N>
+__device__ void warp_svd(FitShared<N>& sh) {
+  const int lane = threadIdx.x & 31;
+  srtrf::svd_init<N>(sh.core, sh.W, lane);
+  __syncwarp();
+  for (int sweep = 0; sweep < srtrf::kSvdMaxSweeps; ++sweep) {
+    bool rotated = false;
+    for (int round = 0; round < srtrf::svd_rounds<N>(); ++round) {
+      const srtrf::SvdRot rot = srtrf::svd_pair<N>(sh.W, round, lane);
+      __syncwarp();
+      srtrf::svd_apply<N>(rot, sh.W, sh.core.V, lane);
+      rotated = rotated || rot.p >= 0;
+      __syncwarp();
+    }
+    if (!__any_sync(0xffffffffu, rotated)) break;
+  }
+  srtrf::svd_values<N>(sh.core, sh.W, sh.qtf, lane);
+  __syncwarp();
+  if (lane == 0) srtrf::svd_finish<N>(sh.core);
+  __syncwarp();
+}
 
 // block-wide sum of NV per-thread values; every thread gets all NV totals.  `parity` alternates between calls so
 // that one barrier per reduction is enough.
@@ -217,10 +241,10 @@ ct_fit_trf_kernel(const double* __restrict__ T, const double* __restrict__ Y, co
     }
     block_qr<N>(A, M, Mp, sh, parity, c.R, sh.qtf);
     double cost_new = 0.0;
-    if (threadIdx.x == 0) {
-      srtrf::svd_setup<N>(c, sh.qtf);
+    __syncthreads();                                           // R and qtf (written by thread 0) visible to warp 0
+    if (threadIdx.x < 32) warp_svd<N>(sh);
+    if (threadIdx.x == 0)
       sh.flag = srtrf::inner_propose<N>(c) ? kFlagTrial : (srtrf::outer_end<N>(c, 0.0) ? kFlagAccept : kFlagReject);
-    }
     __syncthreads();
     while (sh.flag == kFlagTrial) {
       cost_new = eval_cost<N>(pb, c.x_new, sh, parity);       // barrier inside: every thread has read the flag

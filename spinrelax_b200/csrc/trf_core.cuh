@@ -110,48 +110,86 @@ SR_HD void scaling(Core<N>& c) {
 // One-sided (Hestenes) Jacobi SVD of the n x n upper-triangular R:  R V = W with orthogonal columns,
 // s_i = ||W_i||, and s_i (U^T qtf)_i = W_i . qtf.  Accurate to eps * s_max like LAPACK's driver; the order of the
 // singular values is irrelevant to every use below except their extremes.
+//
+// The sweep is organised for one warp: a round-robin tournament pairs the columns so that the (up to four) column
+// pairs of a round are disjoint and rotate at the same time, one group of eight lanes per pair, each lane updating
+// one row of W and V (lane 0 of the group also row 8).  Every round has a read phase (svd_pair: the lanes of a group
+// form the same three column dot products and the same rotation) and a write phase (svd_apply); the caller puts a
+// warp barrier after each.  tests/cpu_harness runs the same two functions lane by lane.
 template <int N>
-SR_HD void svd_setup(Core<N>& c, const double* qtf) {
-  double W[N * N];     // column major: W[j*N + i]
-  for (int j = 0; j < N; ++j)
+SR_HD void svd_init(Core<N>& c, double* W, int lane) {
+  for (int j = lane; j < N; j += 32)
     for (int i = 0; i < N; ++i) {
-      W[j * N + i] = (i <= j) ? c.R[i * N + j] : 0.0;
-      c.V[j * N + i] = (i == j) ? 1.0 : 0.0;      // V column j
+      W[j * N + i] = (i <= j) ? c.R[i * N + j] : 0.0;     // column major: W[j*N + i]
+      c.V[j * N + i] = (i == j) ? 1.0 : 0.0;              // V column j
     }
-  for (int sweep = 0; sweep < 60; ++sweep) {
-    int rotated = 0;
-    for (int p = 0; p < N - 1; ++p)
-      for (int q = p + 1; q < N; ++q) {
-        double a = 0.0, b = 0.0, g = 0.0;
-        for (int i = 0; i < N; ++i) {
-          a += W[p * N + i] * W[p * N + i];
-          b += W[q * N + i] * W[q * N + i];
-          g += W[p * N + i] * W[q * N + i];
-        }
-        if (g == 0.0 || fabs(g) <= kEps * sqrt(a * b)) continue;
-        rotated = 1;
-        const double zeta = (b - a) / (2.0 * g);
-        const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-        const double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
-        for (int i = 0; i < N; ++i) {
-          const double wp = W[p * N + i], wq = W[q * N + i];
-          W[p * N + i] = cs * wp - sn * wq;
-          W[q * N + i] = sn * wp + cs * wq;
-          const double vp = c.V[p * N + i], vq = c.V[q * N + i];
-          c.V[p * N + i] = cs * vp - sn * vq;
-          c.V[q * N + i] = sn * vp + cs * vq;
-        }
-      }
-    if (!rotated) break;
+}
+
+constexpr int kSvdMaxSweeps = 60;
+
+template <int N>
+SR_HD int svd_rounds() { return (N % 2 == 0) ? N - 1 : N; }
+
+struct SvdRot { int p, q; double cs, sn; };    // p < 0: nothing to do for this lane's group
+
+// read phase of round `round`: the rotation for the column pair of this lane's group
+template <int N>
+SR_HD SvdRot svd_pair(const double* W, int round, int lane) {
+  constexpr int ne = (N % 2 == 0) ? N : N + 1;            // players of the tournament (one dummy when N is odd)
+  constexpr int m = ne - 1;
+  SvdRot r; r.p = -1; r.q = -1; r.cs = 1.0; r.sn = 0.0;
+  const int g = lane >> 3;
+  // pair k of the round: k = 0 -> (ne - 1, round), k >= 1 -> ((round + k) % m, (round - k + m) % m); the pair holding
+  // the dummy column is skipped, the others are numbered 0, 1, 2, 3 for the four lane groups
+  int k = (N % 2 == 0) ? g : g + 1;
+  if (k >= ne / 2) return r;
+  int a = (k == 0) ? ne - 1 : (round + k) % m;
+  int b = (k == 0) ? round : (round - k + m) % m;
+  const int p = a < b ? a : b, q = a < b ? b : a;
+  double aa = 0.0, bb = 0.0, gg = 0.0;
+  for (int i = 0; i < N; ++i) {
+    const double wp = W[p * N + i], wq = W[q * N + i];
+    aa += wp * wp; bb += wq * wq; gg += wp * wq;
   }
-  double smax = 0.0, smin = INFINITY;
-  for (int j = 0; j < N; ++j) {
+  if (gg == 0.0 || fabs(gg) <= kEps * sqrt(aa * bb)) return r;
+  const double zeta = (bb - aa) / (2.0 * gg);
+  const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+  r.cs = 1.0 / sqrt(1.0 + t * t);
+  r.sn = r.cs * t;
+  r.p = p; r.q = q;
+  return r;
+}
+
+// write phase: this lane's rows of the two columns, in W and in V
+template <int N>
+SR_HD void svd_apply(const SvdRot& r, double* W, double* V, int lane) {
+  if (r.p < 0) return;
+  const int row0 = lane & 7;
+  for (int i = row0; i < N; i += 8) {
+    const double wp = W[r.p * N + i], wq = W[r.q * N + i];
+    W[r.p * N + i] = r.cs * wp - r.sn * wq;
+    W[r.q * N + i] = r.sn * wp + r.cs * wq;
+    const double vp = V[r.p * N + i], vq = V[r.q * N + i];
+    V[r.p * N + i] = r.cs * vp - r.sn * vq;
+    V[r.q * N + i] = r.sn * vp + r.cs * vq;
+  }
+}
+
+// after the sweeps: singular values and s * (U^T qtf), one column per lane; then the extremes (lane 0)
+template <int N>
+SR_HD void svd_values(Core<N>& c, const double* W, const double* qtf, int lane) {
+  for (int j = lane; j < N; j += 32) {
     double a = 0.0, u = 0.0;
     for (int i = 0; i < N; ++i) { a += W[j * N + i] * W[j * N + i]; u += W[j * N + i] * qtf[i]; }
     c.s[j] = sqrt(a);
     c.suf[j] = u;
-    smax = fmax(smax, c.s[j]); smin = fmin(smin, c.s[j]);
   }
+}
+
+template <int N>
+SR_HD void svd_finish(Core<N>& c) {
+  double smax = 0.0, smin = INFINITY;
+  for (int j = 0; j < N; ++j) { smax = fmax(smax, c.s[j]); smin = fmin(smin, c.s[j]); }
   c.s_max = smax; c.s_min = smin;
   c.full_rank = (c.m >= N) && (smin > kEps * c.m * smax);
 }

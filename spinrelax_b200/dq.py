@@ -244,12 +244,39 @@ def obtain_exponential_guess(x, y, C1):
     return (x[0] - x[1]) / math.log((y[1] - C1) / (y[0] - C1))
 
 
+DEVICE_OBJECTIVE_MIN_POINTS = 16384
+
+
+class _DeviceObjective:
+    """powell_expdecay for a long curve kept on the GPU (sr_expdecay_chi2): one small launch and an 8-byte read-back per
+    trial tau instead of a pass over 1e5 points on the host.  Same signature as powell_expdecay."""
+
+    def __init__(self, x, y):
+        torch = _lib.require_cuda()
+        self.lib = _lib.load()
+        self.n = len(x)
+        self.x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64)).cuda()
+        self.y = torch.from_numpy(np.ascontiguousarray(y, dtype=np.float64)).cuda()
+        self.work = torch.zeros(136, dtype=torch.float64, device=self.x.device)
+        self.out = torch.zeros(1, dtype=torch.float64, device=self.x.device)
+
+    def __call__(self, pos, *args):
+        _, _, C0, C1 = args
+        A = float(np.ravel(pos)[0])
+        _lib.check(self.lib.sr_expdecay_chi2(self.x.data_ptr(), self.y.data_ptr(), self.n, float(C0), float(C1), A,
+                                             self.work.data_ptr(), self.work.numel(), self.out.data_ptr(),
+                                             _lib.current_stream_ptr()), "sr_expdecay_chi2")
+        return float(self.out.item())
+
+
 def conduct_exponential_fit(xlist, ylist, C0, C1):
-    """1-parameter Powell fit of C0 exp(-x/tau) + C1 (:199-207)."""
+    """1-parameter Powell fit of C0 exp(-x/tau) + C1 (:199-207).  SciPy's Powell runs on the host as in the reference;
+    for long curves (all lag windows: 1e5 points) its objective is evaluated on the device."""
     print('= = Begin exponential fit.')
     guess = obtain_exponential_guess([xlist[0], xlist[1]], [ylist[0], ylist[1]], C1)
     print('= = = guessed initial tau: ', guess)
-    fitOut = fmin_powell(powell_expdecay, guess, args=(xlist, ylist, C0, C1), full_output=True)
+    objective = _DeviceObjective(xlist, ylist) if len(xlist) >= DEVICE_OBJECTIVE_MIN_POINTS else powell_expdecay
+    fitOut = fmin_powell(objective, guess, args=(xlist, ylist, C0, C1), full_output=True)
     tau = np.ravel(fitOut[0])[0]
     print('= = = = Tau obtained: ', tau)
     return tau

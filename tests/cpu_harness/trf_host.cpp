@@ -36,6 +36,24 @@ void qr_host(std::vector<double>& A, int M, double* R, double* qtf) {
   }
 }
 
+// the warp-cooperative SVD of trf_core.cuh, its 32 lanes run one after the other (phases separated as on the device)
+template <int N>
+void svd_host(srtrf::Core<N>& c, const double* qtf) {
+  double W[N * N];
+  for (int lane = 0; lane < 32; ++lane) srtrf::svd_init<N>(c, W, lane);
+  for (int sweep = 0; sweep < srtrf::kSvdMaxSweeps; ++sweep) {
+    bool rotated = false;
+    for (int round = 0; round < srtrf::svd_rounds<N>(); ++round) {
+      srtrf::SvdRot rot[32];
+      for (int lane = 0; lane < 32; ++lane) rot[lane] = srtrf::svd_pair<N>(W, round, lane);
+      for (int lane = 0; lane < 32; ++lane) { srtrf::svd_apply<N>(rot[lane], W, c.V, lane); rotated = rotated || rot[lane].p >= 0; }
+    }
+    if (!rotated) break;
+  }
+  for (int lane = 0; lane < 32; ++lane) srtrf::svd_values<N>(c, W, qtf, lane);
+  srtrf::svd_finish<N>(c);
+}
+
 template <int N>
 void fit_one(const double* t, const double* y, const double* sig, int L, const double* p0, const double* lo,
              const double* hi, int max_nfev, double* popt, double* Rout, double* cost, int* status) {
@@ -79,7 +97,7 @@ void fit_one(const double* t, const double* y, const double* sig, int L, const d
     for (int i = 0; i < N; ++i) A[(size_t)N * M + L + i] = 0.0;
     double qtf[N];
     qr_host<N>(A, M, c.R, qtf);
-    srtrf::svd_setup<N>(c, qtf);
+    svd_host<N>(c, qtf);
     while (srtrf::inner_propose<N>(c)) {
       cost_new = eval(c.x_new, fn, nullptr, nullptr);
       if (srtrf::inner_judge<N>(c, cost_new, std::isfinite(cost_new))) break;

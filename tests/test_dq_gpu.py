@@ -89,6 +89,36 @@ def test_dq_consecutive_lags_take_the_shared_memory_kernel(N, first, nl, nch, nr
             assert np.allclose(dq._sym3(M[k, c]), np.einsum("ti,tj->ij", blk, blk), rtol=1e-11, atol=1e-18), (k, c)
 
 
+def test_device_powell_objective_equals_the_python_loop():
+    """Long curves evaluate powell_expdecay on the device (sr_expdecay_chi2): the value must be the reference loop's
+    (calculate-dq-distribution.py:199-203) to 1e-13, and the Powell fit must land on the same tau."""
+    import contextlib
+    import io
+    import math
+    from spinrelax_b200 import dq
+    rng = np.random.default_rng(9)
+    n = 40000
+    x = (np.arange(n) + 1.0) * 10.0
+    y = 0.5 * np.exp(-x / 61234.5) + 0.5 + rng.standard_normal(n) * 1e-4
+    obj = dq._DeviceObjective(x, y)
+    for A in (10.0, 5000.0, 61234.5, 3e6):
+        loop = 0.0
+        for i in range(n):
+            loop += (0.5 * math.exp(-x[i] / A) + 0.5 - y[i]) ** 2
+        loop /= n
+        assert rel_err(obj([A], x, y, 0.5, 0.5), loop) < 1e-13
+        assert rel_err(dq.powell_expdecay([A], x, y, 0.5, 0.5), loop) < 1e-13
+    with contextlib.redirect_stdout(io.StringIO()):
+        tau_dev = dq.conduct_exponential_fit(x, y, 0.5, 0.5)
+        old = dq.DEVICE_OBJECTIVE_MIN_POINTS
+        dq.DEVICE_OBJECTIVE_MIN_POINTS = 10 ** 9
+        try:
+            tau_host = dq.conduct_exponential_fit(x, y, 0.5, 0.5)
+        finally:
+            dq.DEVICE_OBJECTIVE_MIN_POINTS = old
+    assert rel_err(tau_dev, tau_host) < 1e-9 and abs(tau_dev / 61234.5 - 1) < 1e-2
+
+
 def test_dq_curves_and_D_vs_oracle():
     """Anisotropic walk: curves to 1e-12, then the same SciPy Powell gives tau and D to 1e-6; q_rot up to sign."""
     from spinrelax_b200 import dq, synth
