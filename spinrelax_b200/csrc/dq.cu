@@ -20,11 +20,11 @@ constexpr int kDqTile = kDqThreads * kDqPerThread;   // frames per CTA (vec_mome
 constexpr int kDqLagTile = 16;                       // lags per CTA (dq_moments_kernel)
 constexpr int kDqFrameTile = 1024;                   // frames per CTA (dq_moments_kernel)
 constexpr int kDqU = 4;                              // q(t + delta) loads in flight per thread (x2: double buffered)
-constexpr int kDqSuper = 4;                          // frame tiles per super tile of the consecutive-lag kernel
+constexpr int kDqSuper = 8;                          // frame tiles per super tile of the consecutive-lag kernel
 constexpr int kDqSuperFrames = kDqSuper * kDqFrameTile;
 
 // A (lag tile, super tile) is "interior" when the 16 lags of the tile are consecutive integers d0 .. d0 + 15, every
-// pair (t, t + delta) of the 4096-frame super tile exists for all of them, and for each lag the whole super tile
+// pair (t, t + delta) of the 8192-frame super tile exists for all of them, and for each lag the whole super tile
 // falls into one sub-chunk.  dq_moments_consec_kernel reduces interior super tiles with its shared-memory fast path
 // and everything else (edges of the trajectory, sub-chunk boundaries) with the generic tile routine.
 __device__ __forceinline__ bool dq_lag_interior(long long N, long long delta, long long lo, int nCh, int nRep, int replica) {
@@ -140,17 +140,33 @@ dq_moments_kernel(const float4* __restrict__ q, long long N, const long long* __
 }
 
 // Consecutive lags (the "all windows" lag list 1, 2, 3, ...): CTA = (tile of 16 consecutive lags d0 .. d0 + 15, super tile
-// of 4096 frames), interior tiles only (dq_super_interior).  Both operands come from shared memory as float64 planes
-// converted ONCE per CTA -- q(t) for the frame tile and q(t + d0 ...) for the 1024 + 16 frames the 16 lags reach -- so the
-// loop has no global load and no F2F: per pair 18 FP64 instructions and 3.5 shared-memory doubles.  Thread = (lag group
-// g of 4 lags, frame lane): in one step it takes the 2 consecutive frames 2 lane, 2 lane + 1 of a 128-frame slab against
-// its 4 lags, i.e. 8 pairs from 2 left and 5 right quaternions (LDS.128 on 16-byte lane strides: conflict free).  The 24
-// moment sums of a thread live in registers for the whole super tile; warp shuffle reduction, then one FP64 atomic per
-// (lag, moment) and warp.
-constexpr int kDqcPlaneA = kDqFrameTile;
-constexpr int kDqcPlaneB = kDqFrameTile + kDqLagTile;
+// of 8192 frames).  Interior super tiles take the fast path: both operands come from shared memory as float64 planes
+// converted ONCE per CTA -- q(t) for a 1024-frame tile and q(t + d0 ...) for the 1024 + 16 frames the 16 lags reach -- so
+// the loop has no global load and no F2F.  Thread = (lag group g of 4 lags, frame lane owning 16 consecutive frames): it
+// walks its frames two at a time and keeps a sliding window of six right quaternions in registers, so a step of 8
+// pairs (2 frames x 4 lags, 144 FP64 instructions) loads one new pair of left and one new pair of right quaternions:
+// 16 shared-memory bytes per pair.  Planes are padded by 2 doubles every 16 (lane stride 18 doubles: an LDS.128 of a
+// quarter warp touches all 32 banks once).  The 24 moment sums of a thread live in registers for the whole super
+// tile; warp shuffle reduction, then one FP64 atomic per (lag, moment) and warp.
+__host__ __device__ constexpr int dq_pad(int i) { return i + 2 * (i >> 4); }
+constexpr int kDqcPlaneA = dq_pad(kDqFrameTile);
+constexpr int kDqcPlaneB = dq_pad(kDqFrameTile + 2 * kDqLagTile);     // window reaches 16 lags + the look-ahead pair
 constexpr int kDqcSmemDoubles = 4 * kDqcPlaneA + 4 * kDqcPlaneB;
 static_assert(kDqcSmemDoubles >= 4 * (kDqFrameTile + 16 * kDqU), "the generic tile routine borrows this buffer");
+static_assert(kDqcPlaneA % 2 == 0 && kDqcPlaneB % 2 == 0, "planes must keep 16-byte alignment");
+
+struct DqQuatPair { double w[2], x[2], y[2], z[2]; };
+
+__device__ __forceinline__ DqQuatPair dq_load_pair(const double* __restrict__ plane0, int planeStride, int i) {
+  const double* p = plane0 + dq_pad(i);
+  const double2 w = *reinterpret_cast<const double2*>(p);
+  const double2 x = *reinterpret_cast<const double2*>(p + planeStride);
+  const double2 y = *reinterpret_cast<const double2*>(p + 2 * planeStride);
+  const double2 z = *reinterpret_cast<const double2*>(p + 3 * planeStride);
+  DqQuatPair r;
+  r.w[0] = w.x; r.w[1] = w.y; r.x[0] = x.x; r.x[1] = x.y; r.y[0] = y.x; r.y[1] = y.y; r.z[0] = z.x; r.z[1] = z.y;
+  return r;
+}
 
 __global__ void __launch_bounds__(kDqThreads, 2)
 dq_moments_consec_kernel(const float4* __restrict__ q, long long N, const long long* __restrict__ lags, long long d_first,
@@ -175,7 +191,7 @@ dq_moments_consec_kernel(const float4* __restrict__ q, long long N, const long l
     }
     return;
   }
-  const int g = threadIdx.x >> 6, lane = threadIdx.x & 63;          // lag group (4 lags), frame lane
+  const int g = threadIdx.x >> 6, lane = threadIdx.x & 63;          // lag group (4 lags), frame lane (16 frames)
   double acc[4][6];
 #pragma unroll
   for (int j = 0; j < 4; ++j)
@@ -185,54 +201,60 @@ dq_moments_consec_kernel(const float4* __restrict__ q, long long N, const long l
   for (int sub = 0; sub < kDqSuper; ++sub) {
     const long long lo = lo0 + (long long)sub * kDqFrameTile;
     __syncthreads();                                                // previous tile fully consumed
-    for (int i = threadIdx.x; i < kDqcPlaneB; i += kDqThreads) {
-      const float4 b = __ldg(q + lo + d0 + i);                      // interior: lo + d0 + i < N always
-      B[i] = (double)b.x; B[kDqcPlaneB + i] = (double)b.y; B[2 * kDqcPlaneB + i] = (double)b.z; B[3 * kDqcPlaneB + i] = (double)b.w;
-      if (i < kDqcPlaneA) {
-        const float4 a = __ldg(q + lo + i);
-        A[i] = (double)a.x; A[kDqcPlaneA + i] = (double)a.y; A[2 * kDqcPlaneA + i] = (double)a.z; A[3 * kDqcPlaneA + i] = (double)a.w;
+    {
+      // all global loads of the tile first (one exposed L2 latency instead of five), then the conversions
+      constexpr int kNB = (kDqFrameTile + 2 * kDqLagTile + kDqThreads - 1) / kDqThreads;     // 5
+      constexpr int kNA = kDqFrameTile / kDqThreads;                                         // 4
+      float4 rb[kNB], ra[kNA];
+#pragma unroll
+      for (int u = 0; u < kNB; ++u) {
+        const int i = threadIdx.x + u * kDqThreads;
+        const long long tb = lo + d0 + i;                           // interior: tb < N for i < 1024 + 16; the look-ahead
+        rb[u] = (i < kDqFrameTile + 2 * kDqLagTile && tb < N) ? __ldg(q + tb) : make_float4(0.f, 0.f, 0.f, 0.f);   // pair beyond is unused
+      }
+#pragma unroll
+      for (int u = 0; u < kNA; ++u) ra[u] = __ldg(q + lo + threadIdx.x + u * kDqThreads);
+#pragma unroll
+      for (int u = 0; u < kNB; ++u) {
+        const int i = threadIdx.x + u * kDqThreads;
+        if (i < kDqFrameTile + 2 * kDqLagTile) {
+          const int ib = dq_pad(i);
+          B[ib] = (double)rb[u].x; B[kDqcPlaneB + ib] = (double)rb[u].y; B[2 * kDqcPlaneB + ib] = (double)rb[u].z;
+          B[3 * kDqcPlaneB + ib] = (double)rb[u].w;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kNA; ++u) {
+        const int ia = dq_pad(threadIdx.x + u * kDqThreads);
+        A[ia] = (double)ra[u].x; A[kDqcPlaneA + ia] = (double)ra[u].y; A[2 * kDqcPlaneA + ia] = (double)ra[u].z;
+        A[3 * kDqcPlaneA + ia] = (double)ra[u].w;
       }
     }
     __syncthreads();
-#pragma unroll 1
-    for (int slab = 0; slab < kDqFrameTile / 128; ++slab) {
-      const int f = slab * 128 + 2 * lane;                          // this thread's two frames f, f + 1
-      double aw[2], ax[2], ay[2], az[2];
-      {
-        const double2 w = *reinterpret_cast<const double2*>(A + f);
-        const double2 x = *reinterpret_cast<const double2*>(A + kDqcPlaneA + f);
-        const double2 y = *reinterpret_cast<const double2*>(A + 2 * kDqcPlaneA + f);
-        const double2 z = *reinterpret_cast<const double2*>(A + 3 * kDqcPlaneA + f);
-        aw[0] = w.x; aw[1] = w.y; ax[0] = x.x; ax[1] = x.y; ay[0] = y.x; ay[1] = y.y; az[0] = z.x; az[1] = z.y;
-      }
-      // right quaternions: frames f + 4 g .. f + 4 g + 4 relative to the B window (B[i] = q(lo + d0 + i))
-      double bw[5], bx[5], by[5], bz[5];
-      {
-        const int s = f + 4 * g;
-        const double* p = B + s;
+    const int f0 = 16 * lane;                                       // this thread's frames f0 .. f0 + 15 of the tile
+    const int b0 = f0 + 4 * g;                                      // B[i] = q(lo + d0 + i): lag 4 g + j of frame f is B[f + 4 g + j]
+    DqQuatPair w0 = dq_load_pair(B, kDqcPlaneB, b0), w1 = dq_load_pair(B, kDqcPlaneB, b0 + 2), w2;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const double* pc = p + c * kDqcPlaneB;
-          const double2 u0 = *reinterpret_cast<const double2*>(pc);
-          const double2 u1 = *reinterpret_cast<const double2*>(pc + 2);
-          const double u2 = pc[4];
-          double* dst = c == 0 ? bw : c == 1 ? bx : c == 2 ? by : bz;
-          dst[0] = u0.x; dst[1] = u0.y; dst[2] = u1.x; dst[3] = u1.y; dst[4] = u2;
-        }
-      }
+    for (int step = 0; step < 8; ++step) {
+      const DqQuatPair a = dq_load_pair(A, kDqcPlaneA, f0 + 2 * step);
+      w2 = dq_load_pair(B, kDqcPlaneB, b0 + 2 * step + 4);
+      // window: right quaternions e + j for frame e in {0, 1} and lag j in 0..3 -> entries 0..4 of (w0, w1, w2)
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-          const double w2 = bw[e + j], x2 = bx[e + j], y2 = by[e + j], z2 = bz[e + j];
-          // vector part of conj(a) * b, same expression tree as dq_moments_kernel
-          const double vx = fma(aw[e], x2, fma(-w2, ax[e], fma(az[e], y2, -(ay[e] * z2))));
-          const double vy = fma(aw[e], y2, fma(-w2, ay[e], fma(ax[e], z2, -(az[e] * x2))));
-          const double vz = fma(aw[e], z2, fma(-w2, az[e], fma(ay[e], x2, -(ax[e] * y2))));
+          const int k = e + j;                                      // 0 .. 4
+          const DqQuatPair& wp = k < 2 ? w0 : (k < 4 ? w1 : w2);
+          const double w2_ = wp.w[k & 1], x2 = wp.x[k & 1], y2 = wp.y[k & 1], z2 = wp.z[k & 1];
+          // vector part of conj(a) * b, same expression tree as the generic routine
+          const double vx = fma(a.w[e], x2, fma(-w2_, a.x[e], fma(a.z[e], y2, -(a.y[e] * z2))));
+          const double vy = fma(a.w[e], y2, fma(-w2_, a.y[e], fma(a.x[e], z2, -(a.z[e] * x2))));
+          const double vz = fma(a.w[e], z2, fma(-w2_, a.z[e], fma(a.y[e], x2, -(a.x[e] * y2))));
           acc[j][0] = fma(vx, vx, acc[j][0]); acc[j][1] = fma(vx, vy, acc[j][1]); acc[j][2] = fma(vx, vz, acc[j][2]);
           acc[j][3] = fma(vy, vy, acc[j][3]); acc[j][4] = fma(vy, vz, acc[j][4]); acc[j][5] = fma(vz, vz, acc[j][5]);
         }
       }
+      w0 = w1; w1 = w2;
     }
   }
   // a warp holds one lag group: reduce its 24 sums and add them to the sub-chunk this super tile lies in

