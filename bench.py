@@ -249,6 +249,8 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device; this path has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner out of the one-JSON-line stdout
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     lib = _lib.load()

@@ -47,7 +47,9 @@ def test_ct_hist_s2_sharded_by_vector_equal_single_gpu(two_gpus):
            ct.calculate_S2_by_outerProduct(v4.reshape(-1, nR, 3), 10.0, 10.0 * nF), ct.average_vectors(v4.reshape(-1, nR, 3), q))
     assert np.array_equal(one[0][0], two[0][0]) and np.array_equal(one[0][1], two[0][1])
     assert np.array_equal(one[1][0], two[1][0])
-    assert np.array_equal(one[2], two[2]) and np.array_equal(one[3], two[3])
+    # the moment kernel tiles (frames x vectors) per launch, so a vector's FP64 sums are added in another order when the
+    # launch holds 4 instead of 7 vectors: equal to rounding, not bit for bit
+    assert np.allclose(one[2], two[2], rtol=1e-12, atol=0) and np.allclose(one[3], two[3], rtol=1e-12, atol=1e-15)
     oCt, _ = ct_oracle.ct_palmer(v4.astype(np.float64))
     assert rel_err(two[0][0], oCt) < 1e-6
     ho, _ = ct_oracle.sphere_histogram(v4.reshape(-1, nR, 3), q)
