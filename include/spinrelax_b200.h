@@ -244,12 +244,14 @@ int sr_relax_eval(int iso, const double* h_D_J, double zeta, double time_fact, d
  * values and right singular vectors as the Jacobian curve_fit decomposes for pcov); d_cost (nR) = 0.5 sum r^2;
  * d_status (nR, 2) = {SciPy termination status, nfev}: 1 gtol, 2 ftol, 3 xtol, 4 ftol and xtol, 0 max_nfev reached
  * (curve_fit raises RuntimeError), -3 p0 outside the bounds, -4 residuals not finite at p0 (both ValueError upstream).
+ * d_chi (nR, may be NULL): mean_k (f(t_k) - y_k)^2 / sigma_k at the solution -- the reference's chi^2 (calc_chiSq,
+ * fitting_Ct_functions.py:272-276; divided by sigma, not sigma^2) for a model whose zeta is 1; inf for failed solves.
  * Curves too long for shared memory need d_work of sr_ct_fit_workspace_bytes() bytes (0 = not needed).
  * ---------------------------------------------------------------------------------------------- */
 size_t sr_ct_fit_workspace_bytes(int nR, long long L, int nParams);
 int sr_ct_fit_trf(const double* d_t, const double* d_y, const double* d_sigma, int nR, long long L, int nParams,
                   const double* d_p0, const double* d_lo, const double* d_hi, int max_nfev, double ftol, double xtol,
-                  double gtol, double* d_popt, double* d_R, double* d_cost, int* d_status, void* d_work,
+                  double gtol, double* d_popt, double* d_R, double* d_cost, int* d_status, double* d_chi, void* d_work,
                   size_t work_bytes, void* stream);
 
 #ifdef __cplusplus

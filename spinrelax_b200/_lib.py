@@ -46,7 +46,7 @@ def _declare(lib):
                               vp, vp, vp, vp, vp, vp, vp, vp, vp]),
         "sr_ct_fit_workspace_bytes": (sz, [i, ll, i]),
         "sr_ct_fit_trf": (i, [vp, vp, vp, i, ll, i, vp, vp, vp, i, _c.c_double, _c.c_double, _c.c_double, vp, vp, vp, vp,
-                              vp, sz, vp]),
+                              vp, vp, sz, vp]),
         "sr_dq_moments": (i, [vp, ll, vp, i, ll, i, vp, vp]),
         "sr_dq_moments_pooled": (i, [vp, ll, vp, i, ll, i, i, i, i, vp, vp]),
         "sr_dq_self": (i, [vp, ll, ll, vp, vp]),

@@ -40,7 +40,10 @@ struct FitShared {
 template <int N>
 __device__ void warp_svd(FitShared<N>& sh) {
   const int lane = threadIdx.x & 31;
-  srtrf::svd_init<N>(sh.core, sh.W, lane);
+  const bool warm = (sh.core.svd_calls % srtrf::kSvdRestart) != 0;
+  __syncwarp();
+  if (lane == 0) sh.core.svd_calls += 1;
+  srtrf::svd_init<N>(sh.core, sh.W, lane, warm);
   __syncwarp();
   for (int sweep = 0; sweep < srtrf::kSvdMaxSweeps; ++sweep) {
     bool rotated = false;
@@ -89,26 +92,31 @@ struct Problem {
 };
 
 // residuals and Jacobian at x into A (column-major, pitch Mp; column N = residuals); returns cost, fills g
-template <int N>
+// CHI: also sum (f - y)^2 / sigma = r^2 / w, the quantity the reference averages into its chi^2 (calc_chiSq,
+// fitting_Ct_functions.py:272-276, quirk G6: divided by sigma, not sigma^2)
+template <int N, bool CHI = false>
 __device__ void eval_jac(const Problem<N>& pb, const double* x, double* A, int Mp, FitShared<N>& sh, int& parity,
-                         double* g, double& cost) {
+                         double* g, double& cost, double* chi_sum = nullptr) {
   srfit::ModelPars<N> mp;
   srfit::prepare<N>(x, mp);
-  double acc[N + 1];
+  double acc[N + 2];
 #pragma unroll
-  for (int i = 0; i <= N; ++i) acc[i] = 0.0;
+  for (int i = 0; i < N + 2; ++i) acc[i] = 0.0;
   for (int k = threadIdx.x; k < pb.L; k += kFitThreads) {
     double row[N];
-    const double r = srfit::residual_and_row<N>(mp, pb.t[k], pb.y[k], pb.weight(k), row);
+    const double w = pb.weight(k);
+    const double r = srfit::residual_and_row<N>(mp, pb.t[k], pb.y[k], w, row);
 #pragma unroll
     for (int i = 0; i < N; ++i) { A[(size_t)i * Mp + k] = row[i]; acc[i] += row[i] * r; }
     A[(size_t)N * Mp + k] = r;
     acc[N] += r * r;
+    if (CHI) acc[N + 1] += r * r / w;
   }
-  block_sum<N, N + 1>(acc, sh, parity);
+  block_sum<N, CHI ? N + 2 : N + 1>(acc, sh, parity);
 #pragma unroll
   for (int i = 0; i < N; ++i) g[i] = acc[i];
   cost = 0.5 * acc[N];
+  if (CHI) *chi_sum = acc[N + 1];
 }
 
 template <int N>
@@ -166,8 +174,8 @@ __global__ void __launch_bounds__(kFitThreads)
 ct_fit_trf_kernel(const double* __restrict__ T, const double* __restrict__ Y, const double* __restrict__ SIG, int L,
                   const double* __restrict__ P0, const double* __restrict__ LO, const double* __restrict__ HI,
                   int max_nfev, double ftol, double xtol, double gtol, double* __restrict__ POPT,
-                  double* __restrict__ ROUT, double* __restrict__ COST, int* __restrict__ STATUS, double* work,
-                  int in_smem) {
+                  double* __restrict__ ROUT, double* __restrict__ COST, int* __restrict__ STATUS,
+                  double* __restrict__ CHI, double* work, int in_smem) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FitShared<N>& sh = *reinterpret_cast<FitShared<N>*>(smem_raw);
   srtrf::Core<N>& c = sh.core;
@@ -207,6 +215,7 @@ ct_fit_trf_kernel(const double* __restrict__ T, const double* __restrict__ Y, co
       for (int i = 0; i < N; ++i) POPT[(size_t)r * N + i] = c.x[i];
       for (int i = 0; i < N * N; ++i) ROUT[(size_t)r * N * N + i] = 0.0;
       COST[r] = INFINITY; STATUS[2 * r] = -3; STATUS[2 * r + 1] = 0;
+      if (CHI) CHI[r] = INFINITY;
     }
     return;
   }
@@ -217,6 +226,7 @@ ct_fit_trf_kernel(const double* __restrict__ T, const double* __restrict__ Y, co
       for (int i = 0; i < N; ++i) POPT[(size_t)r * N + i] = c.x[i];
       for (int i = 0; i < N * N; ++i) ROUT[(size_t)r * N * N + i] = 0.0;
       COST[r] = INFINITY; STATUS[2 * r] = -4; STATUS[2 * r + 1] = 1;
+      if (CHI) CHI[r] = INFINITY;
     }
     return;
   }
@@ -270,13 +280,15 @@ ct_fit_trf_kernel(const double* __restrict__ T, const double* __restrict__ Y, co
     }
   }
   // R factor of the unscaled Jacobian at the solution
-  eval_jac<N>(pb, c.x, A, Mp, sh, parity, g, cost);
+  double chi_sum = 0.0;
+  eval_jac<N, true>(pb, c.x, A, Mp, sh, parity, g, cost, &chi_sum);
   block_qr<N>(A, L, Mp, sh, parity, c.R, sh.qtf);
   if (threadIdx.x == 0) {
     for (int i = 0; i < N; ++i) POPT[(size_t)r * N + i] = c.x[i];
     for (int i = 0; i < N * N; ++i) ROUT[(size_t)r * N * N + i] = c.R[i];
     COST[r] = c.cost;
     STATUS[2 * r] = c.status; STATUS[2 * r + 1] = c.nfev;
+    if (CHI) CHI[r] = chi_sum / (double)L;
   }
 }
 
@@ -288,7 +300,7 @@ size_t fit_smem_bytes(long long L) {
 template <int N>
 int launch_fit(const double* d_t, const double* d_y, const double* d_sigma, int nR, long long L, const double* d_p0,
                const double* d_lo, const double* d_hi, int max_nfev, double ftol, double xtol, double gtol,
-               double* d_popt, double* d_R, double* d_cost, int* d_status, void* d_work, size_t work_bytes,
+               double* d_popt, double* d_R, double* d_cost, int* d_status, double* d_chi, void* d_work, size_t work_bytes,
                cudaStream_t stream) {
   size_t smem = fit_smem_bytes<N>(L);
   int in_smem = smem <= kFitSmemLimit;
@@ -302,8 +314,8 @@ int launch_fit(const double* d_t, const double* d_y, const double* d_sigma, int 
   }
   SR_CUDA(cudaFuncSetAttribute(ct_fit_trf_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFitSmemLimit));
   ct_fit_trf_kernel<N><<<nR, kFitThreads, smem, stream>>>(d_t, d_y, d_sigma, (int)L, d_p0, d_lo, d_hi, max_nfev, ftol,
-                                                           xtol, gtol, d_popt, d_R, d_cost, d_status, (double*)d_work,
-                                                           in_smem);
+                                                           xtol, gtol, d_popt, d_R, d_cost, d_status, d_chi,
+                                                           (double*)d_work, in_smem);
   SR_CUDA(cudaGetLastError());
   return SR_OK;
 }
@@ -320,7 +332,7 @@ extern "C" size_t sr_ct_fit_workspace_bytes(int nR, long long L, int nParams) {
 extern "C" int sr_ct_fit_trf(const double* d_t, const double* d_y, const double* d_sigma, int nR, long long L, int nParams,
                              const double* d_p0, const double* d_lo, const double* d_hi, int max_nfev, double ftol,
                              double xtol, double gtol, double* d_popt, double* d_R, double* d_cost, int* d_status,
-                             void* d_work, size_t work_bytes, void* stream) {
+                             double* d_chi, void* d_work, size_t work_bytes, void* stream) {
   SR_REQUIRE(d_t && d_y && d_p0 && d_lo && d_hi && d_popt && d_R && d_cost && d_status, "sr_ct_fit_trf: null pointer");
   SR_REQUIRE(nR > 0 && L > 0 && L < (1LL << 30), "sr_ct_fit_trf: bad shape (nR=%d L=%lld)", nR, L);
   SR_REQUIRE(nParams >= 2 && nParams <= kMaxP, "sr_ct_fit_trf: nParams %d outside [2, %d]", nParams, kMaxP);
@@ -329,7 +341,7 @@ extern "C" int sr_ct_fit_trf(const double* d_t, const double* d_y, const double*
 #define SR_FIT_CASE(NP)                                                                                            \
   case NP:                                                                                                         \
     return launch_fit<NP>(d_t, d_y, d_sigma, nR, L, d_p0, d_lo, d_hi, max_nfev, ftol, xtol, gtol, d_popt, d_R, d_cost, \
-                          d_status, d_work, work_bytes, (cudaStream_t)stream);
+                          d_status, d_chi, d_work, work_bytes, (cudaStream_t)stream);
   switch (nParams) {
     SR_FIT_CASE(2) SR_FIT_CASE(3) SR_FIT_CASE(4) SR_FIT_CASE(5) SR_FIT_CASE(6) SR_FIT_CASE(7) SR_FIT_CASE(8) SR_FIT_CASE(9)
   }

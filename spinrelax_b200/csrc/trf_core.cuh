@@ -42,6 +42,7 @@ struct Core {
   double step[N], step_h[N], x_new[N];
   double predicted, step_h_norm, step_norm, actual;
   int nfev, max_nfev, status, iteration, m;
+  int svd_calls;        // decompositions since the start of the solve (warm-start bookkeeping)
   double ftol, xtol, gtol;
 };
 
@@ -116,13 +117,28 @@ SR_HD void scaling(Core<N>& c) {
 // one row of W and V (lane 0 of the group also row 8).  Every round has a read phase (svd_pair: the lanes of a group
 // form the same three column dot products and the same rotation) and a write phase (svd_apply); the caller puts a
 // warp barrier after each.  tests/cpu_harness runs the same two functions lane by lane.
+//
+// Warm start: consecutive outer iterations decompose nearly the same matrix, so the sweep starts from W = R V_prev
+// (V_prev = the right vectors of the previous iteration, orthogonal by construction) and needs 2-3 sweeps instead of
+// 6-8.  Every kSvdRestart-th call starts again from V = I so that rounding in V cannot accumulate over a long solve.
+constexpr int kSvdRestart = 24;
+
 template <int N>
-SR_HD void svd_init(Core<N>& c, double* W, int lane) {
-  for (int j = lane; j < N; j += 32)
-    for (int i = 0; i < N; ++i) {
-      W[j * N + i] = (i <= j) ? c.R[i * N + j] : 0.0;     // column major: W[j*N + i]
-      c.V[j * N + i] = (i == j) ? 1.0 : 0.0;              // V column j
-    }
+SR_HD void svd_init(Core<N>& c, double* W, int lane, bool warm) {
+  if (!warm) {
+    for (int j = lane; j < N; j += 32)
+      for (int i = 0; i < N; ++i) {
+        W[j * N + i] = (i <= j) ? c.R[i * N + j] : 0.0;     // column major: W[j*N + i]
+        c.V[j * N + i] = (i == j) ? 1.0 : 0.0;              // V column j
+      }
+    return;
+  }
+  for (int e = lane; e < N * N; e += 32) {                  // W[:, j] = R V_prev[:, j], R upper triangular
+    const int j = e / N, i = e - j * N;
+    double a = 0.0;
+    for (int k = i; k < N; ++k) a += c.R[i * N + k] * c.V[j * N + k];
+    W[j * N + i] = a;
+  }
 }
 
 constexpr int kSvdMaxSweeps = 60;
@@ -366,7 +382,7 @@ SR_HD void select_step(Core<N>& c, double* p_h) {
 template <int N>
 SR_HD void begin(Core<N>& c, int m, int max_nfev, double ftol, double xtol, double gtol) {
   c.m = m; c.max_nfev = max_nfev; c.ftol = ftol; c.xtol = xtol; c.gtol = gtol;
-  c.nfev = 1; c.status = -1; c.iteration = 0; c.alpha = 0.0;
+  c.nfev = 1; c.status = -1; c.iteration = 0; c.alpha = 0.0; c.svd_calls = 0;
   scaling<N>(c);
   double a = 0.0;
   for (int i = 0; i < N; ++i) { const double q = c.x[i] / sqrt(c.v[i]); a += q * q; }

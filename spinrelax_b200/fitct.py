@@ -33,27 +33,59 @@ def curvefit_exponential(DeltaT, *params):
 KERNEL_EVENTS = None      # set to a list to collect (start, end) CUDA event pairs around every sr_ct_fit_trf launch
 
 
-def _device_solve(t, y, sigma, p0, lo, hi):
+class _ResidentCurves:
+    """The (nR, L) curve arrays of a ladder, uploaded once per device and sliced there for every rung (the ladder
+    revisits a shrinking subset of the same residues five times)."""
+
+    def __init__(self, T, Y, SG):
+        self.T, self.Y, self.SG = T, Y, SG
+        self._dev = {}
+
+    def on(self, d):
+        torch = _lib.require_cuda()
+        if d not in self._dev:
+            dev = torch.device("cuda", d)
+            f = lambda x: None if x is None else torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64)).to(dev)  # noqa: E731
+            self._dev[d] = (f(self.T), f(self.Y), f(self.SG))
+        return self._dev[d]
+
+
+def _device_solve(t, y, sigma, p0, lo, hi, resident=None, rows=None):
     """sr_ct_fit_trf on (nR, L) curves: returns popt (nR,nP), the R factor of the Jacobian at the solution (nR,nP,nP),
-    cost (nR,) and status (nR,2) = (SciPy termination status, nfev).  Residues are independent: with several GPUs
-    selected (multigpu.devices) every device solves a contiguous block of them."""
+    cost (nR,), status (nR,2) = (SciPy termination status, nfev) and the reference's chi^2 at the solution (nR,).
+    Residues are independent: with several GPUs selected (multigpu.devices) every device solves a contiguous block of
+    them.  With `resident` (a _ResidentCurves) and `rows` the curves are taken from the device copies instead of t/y/sigma."""
     torch = _lib.require_cuda()
     lib = _lib.load()
     from . import multigpu
-    nR, L = y.shape
-    nP = p0.shape[1]
-    t, lo, hi = np.broadcast_to(t, (nR, L)), np.broadcast_to(lo, (nR, nP)), np.broadcast_to(hi, (nR, nP))
-    sigma = None if sigma is None else np.broadcast_to(sigma, (nR, L))
+    nR, nP = p0.shape
+    if resident is None:
+        L = y.shape[1]
+        t = np.broadcast_to(t, (nR, L))
+        sigma = None if sigma is None else np.broadcast_to(sigma, (nR, L))
+    else:
+        L = resident.Y.shape[1]
+        rows = np.asarray(rows, dtype=np.int64)
+    lo, hi = np.broadcast_to(lo, (nR, nP)), np.broadcast_to(hi, (nR, nP))
 
     def work(d, a, b):
         dev = torch.device("cuda", d)
         f = lambda x: torch.from_numpy(np.array(x[a:b], dtype=np.float64, order='C')).to(dev)   # noqa: E731
         n = b - a
-        td, yd, p0d, lod, hid = f(t), f(y), f(p0), f(lo), f(hi)
-        sd = None if sigma is None else f(sigma)
+        if resident is None:
+            td, yd = f(t), f(y)
+            sd = None if sigma is None else f(sigma)
+        else:
+            Td, Yd, Sd = resident.on(d)
+            idx = torch.from_numpy(rows[a:b]).to(dev)
+            whole = n == Yd.shape[0] and bool(np.array_equal(rows[a:b], np.arange(n)))
+            td, yd = (Td, Yd) if whole else (Td.index_select(0, idx), Yd.index_select(0, idx))
+            sd = None if Sd is None else (Sd if whole else Sd.index_select(0, idx))
+        p0d, lod, hid = f(p0), f(lo), f(hi)
         popt = torch.empty((n, nP), dtype=torch.float64, device=dev)
         R = torch.empty((n, nP, nP), dtype=torch.float64, device=dev)
         cost = torch.empty(n, dtype=torch.float64, device=dev)
+        chi = torch.empty(n, dtype=torch.float64, device=dev)
         status = torch.empty((n, 2), dtype=torch.int32, device=dev)
         wbytes = int(lib.sr_ct_fit_workspace_bytes(n, L, nP))
         work_buf = torch.empty(max(wbytes, 8) // 8, dtype=torch.float64, device=dev) if wbytes else None
@@ -62,16 +94,16 @@ def _device_solve(t, y, sigma, p0, lo, hi):
             ev[0].record()
         _lib.check(lib.sr_ct_fit_trf(td.data_ptr(), yd.data_ptr(), 0 if sd is None else sd.data_ptr(), n, L, nP,
                                      p0d.data_ptr(), lod.data_ptr(), hid.data_ptr(), MAX_NFEV, FTOL, XTOL, GTOL,
-                                     popt.data_ptr(), R.data_ptr(), cost.data_ptr(), status.data_ptr(),
+                                     popt.data_ptr(), R.data_ptr(), cost.data_ptr(), status.data_ptr(), chi.data_ptr(),
                                      0 if work_buf is None else work_buf.data_ptr(), wbytes, _lib.current_stream_ptr()),
                    "sr_ct_fit_trf")
         if KERNEL_EVENTS is not None:
             ev[1].record()
             KERNEL_EVENTS.append(ev)
-        return popt.cpu().numpy(), R.cpu().numpy(), cost.cpu().numpy(), status.cpu().numpy()
+        return popt.cpu().numpy(), R.cpu().numpy(), cost.cpu().numpy(), status.cpu().numpy(), chi.cpu().numpy()
 
     res = multigpu.run(multigpu.plan(nR, min_per_device=32), work)
-    return tuple(np.concatenate([r[k] for r in res], axis=0) for k in range(4))
+    return tuple(np.concatenate([r[k] for r in res], axis=0) for k in range(5))
 
 
 def pcov_from_R(R, cost, L):
@@ -103,13 +135,24 @@ def fit_succeeded(status):
     return np.asarray(status)[..., 0] > 0
 
 
-def gpu_curve_fit(t, y, sigma, p0, lo, hi):
+def gpu_curve_fit(t, y, sigma, p0, lo, hi, **resident):
     """Batched bounded least squares.  t, y, sigma: (nR, L) (sigma may be None); p0, lo, hi: (nR, nP).
-    Returns popt (nR,nP), pcov (nR,nP,nP) formed like scipy.optimize.curve_fit, cost (nR,), status (nR,2);
-    rows with fit_succeeded(status) False are the ones curve_fit would have raised on."""
-    t, y, p0 = np.atleast_2d(t), np.atleast_2d(y), np.atleast_2d(p0)
-    popt, R, cost, status = _device_solve(t, y, sigma, p0, lo, hi)
-    return popt, pcov_from_R(R, cost, y.shape[1]), cost, status
+    Returns popt (nR,nP), pcov (nR,nP,nP) formed like scipy.optimize.curve_fit, cost (nR,), status (nR,2) and the
+    reference's chi^2 of the solution for zeta = 1 (nR,); rows with fit_succeeded(status) False are the ones curve_fit
+    would have raised on.  `resident=..., rows=...`: see _device_solve."""
+    p0 = np.atleast_2d(p0)
+    if not resident:
+        t, y = np.atleast_2d(t), np.atleast_2d(y)
+    out = _device_solve(t, y, sigma, p0, lo, hi, **resident)
+    popt, R, cost, status = out[:4]
+    L = resident["resident"].Y.shape[1] if resident else y.shape[1]
+    return (popt, pcov_from_R(R, cost, L), cost, status) + tuple(out[4:5])
+
+
+_REAL_SOLVERS = None      # (gpu_curve_fit, _device_solve) as defined here; tests swap either for a CPU stand-in
+
+
+_REAL_SOLVERS = (gpu_curve_fit, _device_solve)
 
 
 # ---- containers ------------------------------------------------------------------------------------
@@ -296,7 +339,7 @@ class autoCorrelationModel:
         lo, hi = self.get_bounds_as_list(tauMax=DeltaT[-1] * 10)
         p0 = np.array(self.get_params_as_list(), dtype=float)
         popt, pcov, cost, status = gpu_curve_fit(DeltaT, Decay, dDecay, p0[None, :], np.full_like(p0, lo)[None, :],
-                                                 np.array(hi, dtype=float)[None, :])
+                                                 np.array(hi, dtype=float)[None, :])[:4]
         if not fit_succeeded(status)[0]:
             print("= = = WARNING, curve fitting of %s with %i params failed!" % (self.name, self.nParams), file=fp)
             return np.inf, [False, True, True]
@@ -444,6 +487,8 @@ class autoCorrelations:
         last = {key: val.copy() for key, val in best.items()}        # state of the last rung tried (for residues never accepted)
         active = np.arange(n)
         lines = []
+        resident = None
+        used_device_chi = False
         for nParams in listDoG:
             if active.size == 0:
                 break
@@ -455,7 +500,15 @@ class autoCorrelations:
             p0 = np.concatenate((C0, tau0) + ((S20[:, None],) if fast else ()), axis=1)
             hi = np.concatenate((np.ones((a.size, nc)), np.repeat((T[a, -1] * 10)[:, None], nc, axis=1)) +
                                 ((np.ones((a.size, 1)),) if fast else ()), axis=1)
-            popt, pcov, cost, status = gpu_curve_fit(T[a], Y[a], None if SG is None else SG[a], p0, np.zeros_like(p0), hi)
+            if (gpu_curve_fit, _device_solve) == _REAL_SOLVERS:       # curves stay on the device across the rungs
+                if resident is None:
+                    resident = _ResidentCurves(T, Y, SG)
+                res = gpu_curve_fit(None, None, None, p0, np.zeros_like(p0), hi, resident=resident, rows=a)
+            else:
+                res = gpu_curve_fit(T[a], Y[a], None if SG is None else SG[a], p0, np.zeros_like(p0), hi)
+            popt, pcov, cost, status = res[:4]
+            chi_dev = res[4] if len(res) > 4 and np.all(zeta[a] == 1.0) else None
+            used_device_chi = used_device_chi or chi_dev is not None
             finite = fit_succeeded(status)                            # False where curve_fit raises upstream (:325-328)
             with np.errstate(invalid="ignore"):
                 dParam = np.sqrt(np.diagonal(pcov, axis1=1, axis2=2))
@@ -466,26 +519,9 @@ class autoCorrelations:
                 q_sum = ~((S2_state + sumC0) > 1.0)
                 C, tau = popt[:, :nc], popt[:, nc:2 * nc]
                 S2 = popt[:, -1] if fast else 1.0 - np.sum(C, axis=1)
-                # model = zeta (S2 + sum_c C_c exp(-t / tau_c)), one component at a time in two (n, L) arrays: the
-                # same operations in the same order as the (n, nc, L) broadcast, without its temporaries
-                Ta = T if a.size == n else T[a]
-                ntau = -tau                                   # t / (-tau) == (-1.0 * t) / tau exactly
-                model = np.empty_like(Ta)
-                buf = np.empty_like(Ta) if nc > 1 else None
-                for c in range(nc):
-                    dst = model if c == 0 else buf
-                    np.divide(Ta, ntau[:, c:c + 1], out=dst)
-                    np.exp(dst, out=dst)
-                    np.multiply(C[:, c:c + 1], dst, out=dst)
-                    if c:
-                        model += buf
-                model += S2[:, None]
-                model *= zeta[a][:, None]
-                model -= Y if a.size == n else Y[a]
-                np.square(model, out=model)
-                if SG is not None:
-                    model /= SG if a.size == n else SG[a]
-                chi = np.mean(model, axis=1)
+                chi = chi_dev if chi_dev is not None else _chi_rows(
+                    T if a.size == n else T[a], Y if a.size == n else Y[a],
+                    None if SG is None else (SG if a.size == n else SG[a]), C, tau, S2, zeta[a])
             chi = np.where(finite, chi, np.inf)
             q_over, q_sum = np.where(finite, q_over, True), np.where(finite, q_sum, True)
             ok = finite & q_over & q_sum
@@ -528,6 +564,16 @@ class autoCorrelations:
             active = a[still]
         if lines:
             print("\n".join(lines), file=fp)
+        if used_device_chi:
+            # the rung decisions and the log used the kernel's chi^2 (same quantity, summed in another order); the value
+            # kept with each model is the reference's own arithmetic, evaluated once for the rung that was kept
+            for src in (best, last):
+                for nParams in listDoG:
+                    rows = np.nonzero(src["fit"] & (src["nParams"] == nParams))[0]
+                    if rows.size:
+                        nc = int(nParams / 2)
+                        src["chi"][rows] = _chi_rows(T[rows], Y[rows], None if SG is None else SG[rows], src["C"][rows, :nc],
+                                                     src["tau"][rows, :nc], src["S2"][rows], zeta[rows])
         out = np.full(n, np.inf)
         for i, k in enumerate(keys):
             src = last if first[i] else best
@@ -572,7 +618,7 @@ class autoCorrelations:
                 his.append(m.get_bounds_as_list(tauMax=T[i][-1] * 10)[1])
             p0s, his = np.array(p0s, dtype=float), np.array(his, dtype=float)
             popt, pcov, cost, status = gpu_curve_fit(T[active], Y[active], None if SG is None else SG[active], p0s,
-                                                     np.zeros_like(p0s), his)
+                                                     np.zeros_like(p0s), his)[:4]
             still = []
             for j, i in enumerate(active):
                 k = keys[i]
@@ -604,6 +650,31 @@ class autoCorrelations:
             else:
                 work[k].copy_from(prev[k])
         return np.array([work[k].chiSq if work[k].bHasFit else np.inf for k in keys])
+
+
+def _chi_rows(Ta, Ya, SGa, C, tau, S2, zeta):
+    """calc_chiSq (fitting_Ct_functions.py:272-276) for a stack of residues: mean((zeta model - y)^2 [/ sigma]) with
+    model = S2 + sum_c C_c exp(-t / tau_c), one component at a time in two (n, L) arrays -- the same operations in the
+    same order as the reference's (nc, L) broadcast per residue, without its temporaries."""
+    nc = C.shape[1]
+    ntau = -tau                                   # t / (-tau) == (-1.0 * t) / tau exactly
+    model = np.empty_like(Ta)
+    buf = np.empty_like(Ta) if nc > 1 else None
+    with np.errstate(all="ignore"):
+        for c in range(nc):
+            dst = model if c == 0 else buf
+            np.divide(Ta, ntau[:, c:c + 1], out=dst)
+            np.exp(dst, out=dst)
+            np.multiply(C[:, c:c + 1], dst, out=dst)
+            if c:
+                model += buf
+        model += S2[:, None]
+        model *= zeta[:, None]
+        model -= Ya
+        np.square(model, out=model)
+        if SGa is not None:
+            model /= SGa
+        return np.mean(model, axis=1)
 
 
 def _as_name(k):

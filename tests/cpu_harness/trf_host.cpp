@@ -40,7 +40,9 @@ void qr_host(std::vector<double>& A, int M, double* R, double* qtf) {
 template <int N>
 void svd_host(srtrf::Core<N>& c, const double* qtf) {
   double W[N * N];
-  for (int lane = 0; lane < 32; ++lane) srtrf::svd_init<N>(c, W, lane);
+  const bool warm = (c.svd_calls % srtrf::kSvdRestart) != 0;
+  c.svd_calls += 1;
+  for (int lane = 0; lane < 32; ++lane) srtrf::svd_init<N>(c, W, lane, warm);
   for (int sweep = 0; sweep < srtrf::kSvdMaxSweeps; ++sweep) {
     bool rotated = false;
     for (int round = 0; round < srtrf::svd_rounds<N>(); ++round) {

@@ -60,6 +60,7 @@ def test_device_solve_marshals_arguments_as_the_header_declares(monkeypatch):
             view(a["d_R"], (nR, nP, nP))[:] = np.eye(nP)[None] * np.arange(1, nR + 1)[:, None, None]
             view(a["d_cost"], (nR,))[:] = np.arange(nR) + 0.5
             view(a["d_status"], (nR, 2), ctypes.c_int32, np.int32)[:] = [[1, 7]] * nR
+            view(a["d_chi"], (nR,))[:] = np.arange(nR) * 0.25
             return 0
 
     class FakeTorch:
@@ -80,7 +81,8 @@ def test_device_solve_marshals_arguments_as_the_header_declares(monkeypatch):
     nR, L, nP = 4, 11, 5
     t, y, sg = np.arange(1.0, L + 1), rng.random((nR, L)), rng.random((nR, L)) + 0.1
     p0, hi = rng.random((nR, nP)), np.full((nR, nP), 9.0)
-    popt, Rf, cost, status = fitct._device_solve(np.atleast_2d(t), y, sg, p0, np.zeros_like(p0), hi)
+    popt, Rf, cost, status, chi = fitct._device_solve(np.atleast_2d(t), y, sg, p0, np.zeros_like(p0), hi)
+    assert np.array_equal(chi, np.arange(nR) * 0.25)
     assert (seen["nR"], seen["L"], seen["nP"]) == (nR, L, nP)
     assert seen["max_nfev"] == fitct.MAX_NFEV == 0 and (seen["ftol"], seen["xtol"], seen["gtol"]) == (1e-8, 1e-8, 1e-8)
     assert seen["work_bytes"] == 0 and not seen["work"]
@@ -90,5 +92,5 @@ def test_device_solve_marshals_arguments_as_the_header_declares(monkeypatch):
     assert np.array_equal(popt, p0 + 1.0) and np.array_equal(cost, np.arange(nR) + 0.5)
     assert np.array_equal(Rf[2], 3.0 * np.eye(nP)) and np.array_equal(status, [[1, 7]] * nR)
     # and through the public wrapper: covariance from those R factors (J^T J = R^T R = 4 I for row 1) and costs
-    popt2, pcov, cost2, _ = fitct.gpu_curve_fit(t, y, sg, p0, np.zeros_like(p0), hi)
+    popt2, pcov, cost2, _, _ = fitct.gpu_curve_fit(t, y, sg, p0, np.zeros_like(p0), hi)
     assert np.allclose(pcov[1], np.eye(nP) / 4.0 * (2.0 * 1.5 / (L - nP)))
