@@ -208,6 +208,13 @@ int sr_vec_second_moments(const double* d_v, long long n, int nCh, double* d_M, 
 int sr_jomega_f64(const double* d_x, const double* d_y, double* d_out, long long n, void* stream);
 int sr_jomega_f32(const float* d_x, const float* d_y, float* d_out, long long n, void* stream);
 
+/* The same for the inner loop of a NumPy ufunc (the reference registers double_Jomega / float_Jomega with
+ * PyUFunc_FromFuncAndData, Jomega/Jomega.c:49-104, 135-156): host pointers with byte strides exactly as NumPy hands them
+ * to a loop function (stride 0 = broadcast scalar).  Gather, H2D, kernel, D2H, scatter.  Bound by
+ * spinrelax_b200/csrc/npufunc_module.c, the extension module that makes `npufunc.Jomega` a real numpy.ufunc. */
+int sr_jomega_host_f64(const char* x, long long sx, const char* y, long long sy, char* out, long long so, long long n);
+int sr_jomega_host_f32(const char* x, long long sx, const char* y, long long sy, char* out, long long so, long long n);
+
 /* ------------------------------------------------------------------------------------------------
  * K6: J(omega) -> R1 / R2 / NOE with weighted averaging over the bond-vector distribution.
  * Replaces spectral_densities.py: update_A_coefficients :503-523 (caller builds A), calc_Jomega_one :552-557,

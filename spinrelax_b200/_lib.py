@@ -41,6 +41,8 @@ def _declare(lib):
         "sr_xyz_to_rtp_f64": (i, [vp, ll, vp, i, vp]),
         "sr_jomega_f64": (i, [vp, vp, vp, ll, vp]),
         "sr_jomega_f32": (i, [vp, vp, vp, ll, vp]),
+        "sr_jomega_host_f64": (i, [vp, ll, vp, ll, vp, ll, ll]),
+        "sr_jomega_host_f32": (i, [vp, ll, vp, ll, vp, ll, ll]),
         "sr_relax_a_moments": (i, [vp, i, vp, i, i, vp, vp]),
         "sr_relax_eval": (i, [i, dp, _c.c_double, _c.c_double, _c.c_double, _c.c_double, _c.c_double, i, i, i, i, i,
                               vp, vp, vp, vp, vp, vp, vp, vp, vp]),

@@ -13,6 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libspinrelax_b200.so")
 STAMP = LIB + ".stamp"
+UFUNC_EXT = os.path.join(HERE, "_npufunc_ext.so")       # CPython extension: the real numpy.ufunc `npufunc.Jomega`
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -33,7 +34,7 @@ def _digest():
     h = hashlib.sha256()
     files = _sources() + sorted(
         os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))
-    ) + sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".inc")) + \
+    ) + sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".inc", ".c"))) + \
         [os.path.join(HERE, "..", "include", "spinrelax_b200.h")]
     for p in files:
         with open(p, "rb") as fp:
@@ -84,7 +85,7 @@ def build(force=False, verbose=False):
     """Compile every .cu under csrc/ (in parallel) and link them into one shared library. Returns its path."""
     from concurrent.futures import ThreadPoolExecutor
     dig = _digest()
-    if not force and os.path.exists(LIB) and os.path.exists(STAMP):
+    if not force and os.path.exists(LIB) and os.path.exists(UFUNC_EXT) and os.path.exists(STAMP):
         with open(STAMP) as fp:
             if fp.read().strip() == dig:
                 return LIB
@@ -105,9 +106,23 @@ def build(force=False, verbose=False):
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
         raise RuntimeError("nvcc failed linking libspinrelax_b200.so")
+    _build_ufunc_extension()
     with open(STAMP, "w") as fp:
         fp.write(dig)
     return LIB
+
+
+def _build_ufunc_extension():
+    """gcc -shared csrc/npufunc_module.c against CPython + NumPy headers, linked to libspinrelax_b200.so ($ORIGIN rpath)."""
+    import sysconfig
+    import numpy
+    cmd = ["gcc", "-O2", "-shared", "-fPIC", "-o", UFUNC_EXT, os.path.join(CSRC, "npufunc_module.c"),
+           "-I" + sysconfig.get_paths()["include"], "-I" + numpy.get_include(), "-L" + HERE, "-l:libspinrelax_b200.so",
+           "-Wl,-rpath,$ORIGIN"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("gcc failed on npufunc_module.c")
 
 
 if __name__ == "__main__":

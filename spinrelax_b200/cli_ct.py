@@ -23,7 +23,7 @@ import time
 
 import numpy as np
 
-from . import ct, hist, io_formats
+from . import ct, hist, io_formats, resident
 
 
 def build_parser():
@@ -198,56 +198,58 @@ def main(argv=None):
         cat = np.concatenate(vecXHfit, axis=0)
         fit4, ext4 = cat[None], None
 
-    if args.bDoCt:
-        dt = ct.calculate_dt(deltaT, tau_memory)
-        if ext4 is not None:
-            print("= = = Conducting Ct_external using Palmer's approach.")
-            Ct, dCt = ct.calculate_Ct_Palmer(ext4)
-            io_formats.print_sxylist(args.out_pref + '_Ctext.dat', resXH, dt, np.stack((Ct.T, dCt.T), axis=-1))
-        print("= = = Conducting Ct_internal using Palmer's approach.")
-        Ct, dCt = ct.calculate_Ct_Palmer(fit4)
-        io_formats.print_sxylist(args.out_pref + '_Ctint.dat', resXH, dt, np.stack((Ct.T, dCt.T), axis=-1))
+    # C(t), the average vector, the histogram and S2 all read the fitted vectors: one upload for all of them
+    with resident.keep_on_device(fit4):
+        if args.bDoCt:
+            dt = ct.calculate_dt(deltaT, tau_memory)
+            if ext4 is not None:
+                print("= = = Conducting Ct_external using Palmer's approach.")
+                Ct, dCt = ct.calculate_Ct_Palmer(ext4)
+                io_formats.print_sxylist(args.out_pref + '_Ctext.dat', resXH, dt, np.stack((Ct.T, dCt.T), axis=-1))
+            print("= = = Conducting Ct_internal using Palmer's approach.")
+            Ct, dCt = ct.calculate_Ct_Palmer(fit4)
+            io_formats.print_sxylist(args.out_pref + '_Ctint.dat', resXH, dt, np.stack((Ct.T, dCt.T), axis=-1))
 
-    sh = fit4.shape
-    frames = fit4.reshape((sh[0] * sh[1], sh[-2], sh[-1]))          # :535-536
+        sh = fit4.shape
+        frames = fit4.reshape((sh[0] * sh[1], sh[-2], sh[-1]))          # :535-536
 
-    if args.bDoVecAverage:
-        avg = ct.average_vectors(frames, q_rot)
-        io_formats.print_xylist(args.out_pref + '_avgvec.dat', resXH, np.array(avg).T, True)
+        if args.bDoVecAverage:
+            avg = ct.average_vectors(frames, q_rot)
+            io_formats.print_xylist(args.out_pref + '_avgvec.dat', resXH, np.array(avg).T, True)
 
-    if bDoVecDistrib:
-        if not args.bDoVecHist:
-            # calculate-Ct-from-traj.py:586-607: spherical coordinates of every sample, residue first
-            print("= = = Converting vectors into spherical coordinates.")
-            rtp = _spherical_by_residue(frames, q_rot)
-            print("= = = Debug: shape of the spherical vector distribution:", rtp.shape)
+        if bDoVecDistrib:
+            if not args.bDoVecHist:
+                # calculate-Ct-from-traj.py:586-607: spherical coordinates of every sample, residue first
+                print("= = = Converting vectors into spherical coordinates.")
+                rtp = _spherical_by_residue(frames, q_rot)
+                print("= = = Debug: shape of the spherical vector distribution:", rtp.shape)
+                if args.binary:
+                    np.savez_compressed(args.out_pref + '_vecPhiTheta.npz', names=resXH, dataType='PhiTheta',
+                                        axisLabels=['phi', 'theta'], bHistogram=False, data=rtp[..., 1:3])
+                else:
+                    io_formats.print_s3d(args.out_pref + '_vecPhiTheta.dat', resXH, rtp, (1, 2))
+        if args.bDoVecHist:
+            print("= = = Histgrams will use Lambert Cylindrical projection by converting Theta spanning (0,pi) to "
+                  "cos(Theta) spanning (-1,1)")
+            hist_list, edges = hist.sphere_histogram(frames, q_rot, histBinX)
             if args.binary:
-                np.savez_compressed(args.out_pref + '_vecPhiTheta.npz', names=resXH, dataType='PhiTheta',
-                                    axisLabels=['phi', 'theta'], bHistogram=False, data=rtp[..., 1:3])
+                hist.save_vec_histogram(args.out_pref + '_vecHistogram.npz', resXH, hist_list, edges)
             else:
-                io_formats.print_s3d(args.out_pref + '_vecPhiTheta.dat', resXH, rtp, (1, 2))
-    if args.bDoVecHist:
-        print("= = = Histgrams will use Lambert Cylindrical projection by converting Theta spanning (0,pi) to "
-              "cos(Theta) spanning (-1,1)")
-        hist_list, edges = hist.sphere_histogram(frames, q_rot, histBinX)
-        if args.binary:
-            hist.save_vec_histogram(args.out_pref + '_vecHistogram.npz', resXH, hist_list, edges)
-        else:
-            for i in range(nBonds):
-                ofile = args.out_pref + '_vecXH_' + str(resXH[i]) + '.hist'
-                io_formats.print_gplot_hist(ofile, hist_list[i], edges,
-                                            header='# Lamber Cylindrical Histogram over phi,cos(theta).', bSphere=True)
-                print("= = = Written to output: ", ofile)
+                for i in range(nBonds):
+                    ofile = args.out_pref + '_vecXH_' + str(resXH[i]) + '.hist'
+                    io_formats.print_gplot_hist(ofile, hist_list[i], edges,
+                                                header='# Lamber Cylindrical Histogram over phi,cos(theta).', bSphere=True)
+                    print("= = = Written to output: ", ofile)
 
-    if args.bDoS2:
-        if tau_memory is not None:
-            print("= = = Conducting S2 analysis using memory time to chop input-trajectories", tau_memory, "ps")
-            S2 = ct.calculate_S2_by_outerProduct(frames, deltaT, tau_memory)
-        else:
-            print("= = = Conducting S2 analysis directly from trajectories.")
-            S2 = ct.calculate_S2_by_outerProduct(frames)
-        io_formats.print_xylist(args.out_pref + '_S2.dat', resXH, (S2.T) * args.zeta, True)
-        print("      ...complete.")
+        if args.bDoS2:
+            if tau_memory is not None:
+                print("= = = Conducting S2 analysis using memory time to chop input-trajectories", tau_memory, "ps")
+                S2 = ct.calculate_S2_by_outerProduct(frames, deltaT, tau_memory)
+            else:
+                print("= = = Conducting S2 analysis directly from trajectories.")
+                S2 = ct.calculate_S2_by_outerProduct(frames)
+            io_formats.print_xylist(args.out_pref + '_S2.dat', resXH, (S2.T) * args.zeta, True)
+            print("      ...complete.")
 
     print("= = Finished. Total seconds elapsed: %g" % (time.time() - time_start))
 

@@ -180,6 +180,69 @@ extern "C" int sr_jomega_f32(const float* d_x, const float* d_y, float* d_out, l
   return SR_OK;
 }
 
+// Host-strided form for a NumPy ufunc inner loop (Jomega/Jomega.c:49-66 has the signature
+// loop(char** args, npy_intp* dimensions, npy_intp* steps, void*)): gathers the three strided streams, runs the kernel
+// and scatters the result.  Zero strides (broadcast scalars) are honoured.
+namespace {
+// grow-only staging buffers per host thread (NumPy may call a ufunc loop many times with a short inner dimension)
+struct JomegaScratch {
+  void* h = nullptr; void* d = nullptr; size_t cap = 0; int dev = -1;
+  ~JomegaScratch() { if (h) cudaFreeHost(h); if (d) cudaFree(d); }
+};
+thread_local JomegaScratch g_jomega_scratch;
+
+template <typename T, typename K>
+int jomega_host_strided(const char* x, long long sx, const char* y, long long sy, char* out, long long so, long long n,
+                        K launch) {
+  if (n <= 0) return SR_OK;
+  JomegaScratch& sc = g_jomega_scratch;
+  int dev = 0;
+  SR_CUDA(cudaGetDevice(&dev));
+  const size_t need = sizeof(T) * 3 * (size_t)n;
+  cudaError_t e = cudaSuccess;
+  if (sc.cap < need || sc.dev != dev) {
+    if (sc.h) cudaFreeHost(sc.h);
+    if (sc.d) cudaFree(sc.d);
+    sc.h = sc.d = nullptr; sc.cap = 0; sc.dev = dev;
+    const size_t cap = need < 4096 ? 4096 : need;
+    if ((e = cudaMallocHost(&sc.h, cap)) != cudaSuccess || (e = cudaMalloc(&sc.d, cap)) != cudaSuccess) {
+      if (sc.h) cudaFreeHost(sc.h);
+      sc.h = nullptr;
+      sr_set_error("sr_jomega_host: allocation of %lld elements failed: %s", n, cudaGetErrorString(e));
+      return SR_ERR_CUDA;
+    }
+    sc.cap = cap;
+  }
+  T* h = static_cast<T*>(sc.h);
+  T* d = static_cast<T*>(sc.d);
+  for (long long i = 0; i < n; ++i) {
+    h[i] = *reinterpret_cast<const T*>(x + i * sx);
+    h[n + i] = *reinterpret_cast<const T*>(y + i * sy);
+  }
+  int rc = SR_OK;
+  if ((e = cudaMemcpy(d, h, sizeof(T) * 2 * (size_t)n, cudaMemcpyHostToDevice)) == cudaSuccess) {
+    rc = launch(d, d + n, d + 2 * n, n);
+    if (rc == SR_OK) e = cudaMemcpy(h + 2 * n, d + 2 * n, sizeof(T) * (size_t)n, cudaMemcpyDeviceToHost);
+  }
+  if (e != cudaSuccess) { sr_set_error("sr_jomega_host: copy failed: %s", cudaGetErrorString(e)); rc = SR_ERR_CUDA; }
+  if (rc == SR_OK)
+    for (long long i = 0; i < n; ++i) *reinterpret_cast<T*>(out + i * so) = h[2 * n + i];
+  return rc;
+}
+}  // namespace
+
+extern "C" int sr_jomega_host_f64(const char* x, long long sx, const char* y, long long sy, char* out, long long so, long long n) {
+  SR_REQUIRE(x && y && out, "sr_jomega_host_f64: null pointer");
+  return jomega_host_strided<double>(x, sx, y, sy, out, so, n, [](const double* a, const double* b, double* c, long long m) {
+    return sr_jomega_f64(a, b, c, m, nullptr); });
+}
+
+extern "C" int sr_jomega_host_f32(const char* x, long long sx, const char* y, long long sy, char* out, long long so, long long n) {
+  SR_REQUIRE(x && y && out, "sr_jomega_host_f32: null pointer");
+  return jomega_host_strided<float>(x, sx, y, sy, out, so, n, [](const float* a, const float* b, float* c, long long m) {
+    return sr_jomega_f32(a, b, c, m, nullptr); });
+}
+
 extern "C" int sr_relax_a_moments(const double* d_A, int per_residue_A, const double* d_W, int nR, int B,
                                   double* d_amom, void* stream) {
   SR_REQUIRE(d_A && d_W && d_amom, "sr_relax_a_moments: null pointer");

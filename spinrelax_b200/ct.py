@@ -119,8 +119,19 @@ def calculate_Ct_Palmer(vecs, _verbose=True):
     dCt = np.empty((L, nR), dtype=np.float32)
     if L == 0:
         return Ct.astype(out_dtype), dCt.astype(out_dtype)
-    from . import multigpu
+    from . import multigpu, resident
     blocks = multigpu.plan(nR)
+    if resident._REG.get(resident._key(v32)) is not None:
+        # the array is being kept on the device for the stages that follow (resident.keep_on_device): compute from the
+        # device copies, which the histogram / S2 / average-vector stages then reuse
+        def work_dev(dev, a, b):
+            blk = resident.device_block(v32.reshape(nC * nF, nR, 3), dev, a, b).view(nC, nF, b - a, 3)
+            c, d = ct_palmer_device(blk)
+            return c.cpu().numpy(), d.cpu().numpy()
+
+        for (dev, a, b), (c, d) in zip(blocks, multigpu.run(blocks, work_dev)):
+            Ct[:, a:b], dCt[:, a:b] = c, d
+        return Ct.astype(out_dtype, copy=False), dCt.astype(out_dtype, copy=False)
     if len(blocks) == 1:
         with _lib.require_cuda().cuda.device(blocks[0][0]):
             rc = lib.sr_ct_palmer_host(v32.ctypes.data_as(ctypes.c_void_p), nC, nF, nR,
@@ -147,13 +158,13 @@ def _block_moments(vecs3, frames_per_block):
     """GPU sums of x,y,z and the six second moments per (block, vector): (nBlocks, nR, 9) float64."""
     torch = _lib.require_cuda()
     lib = _lib.load()
-    from . import multigpu
+    from . import multigpu, resident
     v = np.asarray(vecs3, dtype=np.float32)
     nFr, nR, _ = v.shape
     nB = -(-nFr // frames_per_block)
 
     def work(dev, a, b):
-        vd = torch.from_numpy(np.ascontiguousarray(v[:, a:b, :])).cuda()
+        vd = resident.device_block(v, dev, a, b)
         out = torch.empty((nB, b - a, 9), dtype=torch.float64, device=vd.device)
         _lib.check(lib.sr_vec_block_moments(vd.data_ptr(), nFr, b - a, int(frames_per_block), out.data_ptr(),
                                             _lib.current_stream_ptr()), "sr_vec_block_moments")

@@ -123,14 +123,14 @@ def sphere_histogram(frames_vecs, q_rot=None, nbins_phi=72):
     promotes) or float32 (no rotation), edges = [phi edges, cos(theta) edges].
     """
     torch = _lib.require_cuda()
-    from . import multigpu
+    from . import multigpu, resident
     v = np.asarray(frames_vecs, dtype=np.float32)
     if v.ndim != 3 or v.shape[-1] != 3:
         raise ValueError("sphere_histogram: expected (frames, nR, 3)")
 
     def work(dev, a, b):        # every vector has its own histogram: shard the vectors, no reduction
         acc = SphereHistogram(b - a, nbins_phi, device=torch.device("cuda", dev))
-        v_dev = torch.from_numpy(np.ascontiguousarray(v[:, a:b, :])).to(acc.dev, non_blocking=True)
+        v_dev = resident.device_block(v, dev, a, b)
         acc.accumulate_device(v_dev, q_rot)
         return acc.finish(v_dev, q_rot), acc.edges_phi, acc.edges_cos
 

@@ -35,6 +35,14 @@ def test_jomega_ufunc(golden):
     assert npufunc.Jomega.nin == 2 and npufunc.Jomega.nout == 1 and 'dd->d' in npufunc.Jomega.types
     big = np.random.default_rng(1).uniform(1e-6, 1, (257, 33))
     assert np.array_equal(npufunc.Jomega(big, big[:1]), sd_oracle.jomega(big, big[:1]))   # broadcasting
+    # a real numpy.ufunc object like the reference's (Jomega.c:135-156): out=, where=, integer inputs promoted to 'dd->d'
+    assert isinstance(npufunc.Jomega, np.ufunc)
+    out = np.full(5, -1.0)
+    r = npufunc.Jomega(np.arange(1.0, 6.0), 2.0, out=out, where=np.array([True, False, True, False, True]))
+    assert r is out and np.array_equal(out[[1, 3]], [-1.0, -1.0]) and out[0] == 1.0 / 5.0 and out[4] == 5.0 / 29.0
+    assert npufunc.Jomega(np.arange(1, 4), 1).dtype == np.float64
+    with pytest.raises(TypeError):
+        npufunc.Jomega(np.ones(2, dtype=np.complex128), 1.0)
 
 
 def test_relaxation_classes_vs_golden(golden, tmp_path):
