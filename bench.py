@@ -45,7 +45,7 @@ def n_pairs(nR, nC, nF, L):
 
 
 def workload_config(n_gpus):
-    if n_gpus > 1:
+    if n_gpus > 1 or os.environ.get("SPINRELAX_BENCH_C4"):
         from spinrelax_b200 import shard
         sizes = shard.split_sizes(C4_N_VEC, n_gpus)
         return {"workload": "BASELINE config 4: %d bond vectors (1000 N-H + 1000 Calpha-Halpha) x 1e6 frames (%d chunks x %d), "
@@ -257,7 +257,8 @@ def run_ours(args):
 
     nC, nF = N_CHUNK, N_FRAMES_PER_CHUNK
     L = nF // 2
-    if world == 1:
+    force_c4 = bool(os.environ.get("SPINRELAX_BENCH_C4"))      # capture config 4 on one GPU too (profiles/, not the default)
+    if world == 1 and not force_c4:
         v_host = torch.from_numpy(make_input(rank)).pin_memory()
         nR = n_total = N_VEC
         v_dev = v_host.to(dev, non_blocking=True)
@@ -307,7 +308,7 @@ def run_ours(args):
     # the reference-signature drop-in itself: calculate_Ct_Palmer(vecs) on an ordinary (pageable) NumPy array through
     # the single C-ABI host call sr_ct_palmer_host (C(t) only: the histogram is a separate call in the reference too)
     dropin_s = None
-    if world == 1:
+    if world == 1 and not force_c4:
         v_page = np.array(v_np)                      # pageable copy
         ct.calculate_Ct_Palmer_quiet(v_page)                # warm-up: sizes the library's scratch cache
         t0 = time.perf_counter()
@@ -337,13 +338,14 @@ def run_ours(args):
 
     secondary = None
     try:
-        secondary = run_secondary(world, rank, local, dev)
+        if not force_c4:
+            secondary = run_secondary(world, rank, local, dev)
     except Exception as exc:                                   # the headline line must survive a secondary failure
         secondary = {"error": "%s: %s" % (type(exc).__name__, exc)}
 
     if rank == 0:
         pairs_gpu = n_pairs(nR, nC, nF, L)                    # rank 0 holds a largest block of the partition
-        pairs_job = n_pairs(n_total, nC, nF, L) if world > 1 else pairs_gpu
+        pairs_job = n_pairs(n_total, nC, nF, L)
         value = pairs_job * args.steps / (ms_total * 1e-3)
         pk = peaks()
         lag_ms = kt["ct_lag_kernel"]
@@ -359,10 +361,10 @@ def run_ours(args):
             gbs = samples * 12 / (kt["sphere_hist_kernel"] * 1e-3) / 1e9
             roof["streaming"] = {"kernel": "sphere_hist_kernel", "bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"],
                                  "unit": "GB/s", "frac": gbs / pk["hbm_gbs"], "bytes_per_sample": 12}
-        cpu = cpu_baseline_single(v_np) if world == 1 else None
+        cpu = cpu_baseline_single(v_np) if (world == 1 and not force_c4) else None
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-                "scaling": "weak" if world == 1 else "strong", "vs_baseline": None, "dtype": "f32 products, f64 accumulation",
+                "scaling": "weak" if (world == 1 and not force_c4) else "strong", "vs_baseline": None, "dtype": "f32 products, f64 accumulation",
                 "data": "synthetic", "config": workload_config(world), "clocks": clocks,
                 "e2e": {"value": pairs_job * e2e_steps / e2e_s, "unit": UNIT,
                         "h2d_bytes_per_step": int(v_np.nbytes), "d2h_bytes_per_step": int(step.d2h_bytes()),

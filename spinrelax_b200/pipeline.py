@@ -159,13 +159,21 @@ class CtHistStep:
             n += self.nR * self.nbx * self.nby * 4
         return n
 
-    @staticmethod
-    def ncu_traffic_bytes():
-        """DRAM bytes per ct_lag_kernel launch from the committed ncu capture (profiles/), or None."""
+    # tile configuration of the ct_lag_kernel instantiation the library launches for long chunks (csrc/ct.cu: CtLong)
+    CT_LAG_CONFIG = "CtCfg<R=19,MB=12,FB=3,NW=12,MINB=1,NS=2,FLUSH=0>"
+
+    @classmethod
+    def ncu_traffic_bytes(cls):
+        """DRAM bytes per ct_lag_kernel launch from the committed ncu capture (profiles/ncu_traffic.json), or None.
+        The capture records the tile configuration it was taken with; a capture of another configuration is not
+        reported as this build's traffic."""
         import json
         import os
         p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "ncu_traffic.json")
-        if os.path.exists(p):
-            with open(p) as fp:
-                return json.load(fp).get("ct_lag_kernel_dram_bytes_per_launch")
-        return None
+        if not os.path.exists(p):
+            return None
+        with open(p) as fp:
+            rec = json.load(fp)
+        if rec.get("kernel_config") != cls.CT_LAG_CONFIG:
+            return None
+        return rec.get("ct_lag_kernel_dram_bytes_per_launch")

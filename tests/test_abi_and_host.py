@@ -407,3 +407,19 @@ def test_call_sites_pass_as_many_arguments_as_the_header_declares():
                 assert len(node.args) == nparams[node.func.attr], (fn, node.lineno, node.func.attr)
                 calls += 1
     assert calls >= 25
+
+
+def test_ncu_traffic_record_is_tied_to_the_shipped_tile_configuration():
+    """roofline.traffic comes from a committed ncu capture: the record names the ct_lag_kernel configuration it was
+    taken with, pipeline reports it only for that configuration, and that configuration is the one csrc/ct.cu ships."""
+    import json
+    import re
+    from conftest import ROOT
+    from spinrelax_b200 import pipeline
+    src = open(os.path.join(ROOT, "spinrelax_b200", "csrc", "ct.cu")).read()
+    m = re.search(r"using CtLong = CtCfg<(\d+), (\d+), (\d+), (\d+), (\d+), (\d+)>;", src)
+    assert m, "CtLong not found"
+    tag = "CtCfg<R=%s,MB=%s,FB=%s,NW=%s,MINB=%s,NS=%s,FLUSH=0>" % m.groups()
+    assert pipeline.CtHistStep.CT_LAG_CONFIG == tag
+    rec = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    assert (pipeline.CtHistStep.ncu_traffic_bytes() is not None) == (rec.get("kernel_config") == tag)
