@@ -38,7 +38,7 @@ def _digest():
         [os.path.join(HERE, "..", "include", "spinrelax_b200.h")]
     for p in files:
         with open(p, "rb") as fp:
-            h.update(p.encode())
+            h.update(os.path.basename(p).encode())      # not the absolute path: the snapshot on the GPU box lives elsewhere
             h.update(fp.read())
     h.update((" ".join(NVCC_FLAGS) + repr(sorted(PER_FILE_FLAGS.items()))).encode())
     return h.hexdigest()
@@ -84,13 +84,32 @@ def build_tuning(out, sources=("ct.cu", "api.cu"), verbose=False):
 def build(force=False, verbose=False):
     """Compile every .cu under csrc/ (in parallel) and link them into one shared library. Returns its path."""
     from concurrent.futures import ThreadPoolExecutor
+    import fcntl
     dig = _digest()
-    if not force and os.path.exists(LIB) and os.path.exists(UFUNC_EXT) and os.path.exists(STAMP):
-        with open(STAMP) as fp:
-            if fp.read().strip() == dig:
-                return LIB
+
+    def fresh():
+        if os.path.exists(LIB) and os.path.exists(UFUNC_EXT) and os.path.exists(STAMP):
+            with open(STAMP) as fp:
+                return fp.read().strip() == dig
+        return False
+
+    if not force and fresh():
+        return LIB
     if not os.path.exists(nvcc_path()) and os.path.sep in nvcc_path():
         raise RuntimeError("libspinrelax_b200.so is missing or stale and nvcc is not available to rebuild it")
+    # one builder at a time (torchrun starts every rank at once): the others wait here and find a fresh library
+    lock = open(LIB + ".lock", "w")
+    fcntl.flock(lock, fcntl.LOCK_EX)
+    try:
+        if not force and fresh():
+            return LIB
+        return _build_locked(dig, verbose, ThreadPoolExecutor)
+    finally:
+        fcntl.flock(lock, fcntl.LOCK_UN)
+        lock.close()
+
+
+def _build_locked(dig, verbose, ThreadPoolExecutor):
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
     jobs = [(s, os.path.join(objdir, os.path.basename(s)[:-3] + ".o"), verbose) for s in _sources()]
