@@ -2,7 +2,8 @@
 one-GPU box these tests skip.
 
  * single process, several devices (spinrelax_b200.multigpu): the public functions shard bond vectors / residues / lags
-   over the selected GPUs -- results must be bit-identical to the one-GPU run, including uneven shares;
+   over the selected GPUs -- C(t), histograms, fits and relaxation must be bit-identical to the one-GPU run (uneven shares included), FP64
+   moment sums equal to rounding;
  * one process per GPU (torch.distributed, NCCL): pipeline.CtHistStep at world 2 gathers C(t), dC(t) and the histogram
    of the whole vector set on rank 0 -- compared with the oracle."""
 import io
@@ -77,7 +78,8 @@ def test_fits_relaxation_dq_sharded_equal_single_gpu(two_gpus):
     assert np.array_equal(c1, c2) and m1 == m2
     for k in ("R1", "R2", "NOE"):
         assert np.array_equal(g1[k][0], g2[k][0])
-    assert np.array_equal(M1, M2)
+    # the moment sums are FP64 atomics over tiles whose grouping depends on the block of the lag list a device gets
+    assert np.max(np.abs(M1 - M2) / np.max(np.abs(M1), axis=(1, 2), keepdims=True)) < 1e-13
 
 
 def _free_port():
