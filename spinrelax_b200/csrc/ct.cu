@@ -37,8 +37,12 @@ namespace {
 //      per thread for a wider window (R up to 33 at 12 warps), at one LDS.64 + STS.64 per flushed sum.
 // DIAG (tuning builds only) removes pieces of the loop to attribute their cost: 1 no flush, 2 no window loads,
 // 3 no left-vector loads, 4 no shared-memory loads at all.  Results are wrong by construction.
-template <int R_, int MB_, int FB_, int NW_, int MINB_, int NS_ = 2, int FLUSH_ = 0, int DIAG_ = 0, int ORDER_ = 0>
+template <int R_, int MB_, int FB_, int NW_, int MINB_, int NS_ = 2, int FLUSH_ = 0, int DIAG_ = 0, int ORDER_ = 0,
+          int SYNC_ = 0>
 struct CtCfg {
+  // SYNC = 1: the warps that share an SM sub-partition (warp % 4) meet at a named barrier before every flush interval, so
+  // that they walk the 25 KB loop body together and share the instruction lines fetched for it
+  static constexpr int SYNC = SYNC_;
   static constexpr int ORDER = ORDER_;    // 0: lag after lag; 1: in phases (R multiplies, R + R dot FMAs, R accumulates); 2: phases, order pinned
   static constexpr int NS = NS_;          // TMA stages in the ring
   static constexpr int R = R_;            // lags per lane (odd)
@@ -75,6 +79,12 @@ __device__ __forceinline__ void ct_block(const float* __restrict__ LX, const flo
   constexpr int kR = Cfg::R;
 #pragma unroll
   for (int kk = 0; kk < kR; ++kk) {
+    // SYNC = G + 1 >= 2: the warps of a sub-partition re-align every G steps (they execute identical instruction streams)
+    // (no memory clobber: the barrier aligns the warps in time only, the loads of the tile may move across it)
+    if (Cfg::SYNC >= 2 && Cfg::SYNC < 10 && kk % (Cfg::SYNC - 1) == 0)
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + (int)((threadIdx.x >> 5) & 3)), "r"(32 * (Cfg::NW / 4)));
+    if (Cfg::SYNC == 10)   // every step, memory clobber kept (reference point)
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + (int)((threadIdx.x >> 5) & 3)), "r"(32 * (Cfg::NW / 4)) : "memory");
     float ax, ay, az, nx, ny, nz;
     if (Cfg::DIAG == 3 || Cfg::DIAG == 4) { ax = wx[(kk + 1) % kR]; ay = wy[(kk + 2) % kR]; az = wz[(kk + 3) % kR]; }
     else { ax = LX[s + kk]; ay = LY[s + kk]; az = LZ[s + kk]; }                  // u(t), broadcast
@@ -88,6 +98,8 @@ __device__ __forceinline__ void ct_block(const float* __restrict__ LX, const flo
     if (Cfg::ORDER == 0) {
 #pragma unroll
       for (int j = 0; j < kR; ++j) {
+        if (Cfg::SYNC == 11 && (j == 0 || j == kR / 2))
+          asm volatile("bar.sync %0, %1;" ::"r"(1 + (int)((threadIdx.x >> 5) & 3)), "r"(32 * (Cfg::NW / 4)));
         const int sl = (kk + j) % kR;              // slot holding frame t + d0 + o + j
         float d = ax * wx[sl];
         d = fmaf(ay, wy[sl], d);
@@ -203,7 +215,9 @@ ct_lag_kernel(const float* __restrict__ U, long long pitch, int nF, int L, int n
     const float* __restrict__ WY = WX + kTW;
     const float* __restrict__ WZ = WY + kTW;
 
-    if (k * kTF + s0 < nSteps) {   // warp-uniform: whole warp range is past the last valid pair otherwise
+    // warp-uniform: the whole warp range is past the last valid pair otherwise.  With SYNC the test is CTA-uniform (the
+    // warps of a sub-partition must reach the same barriers; the extra frames are zero padding and add nothing)
+    if (k * kTF + (Cfg::SYNC ? 0 : s0) < nSteps) {
       float wx[kR], wy[kR], wz[kR];
 #pragma unroll
       for (int j = 0; j < kR; ++j) {
@@ -211,6 +225,7 @@ ct_lag_kernel(const float* __restrict__ U, long long pitch, int nF, int L, int n
       }
 #pragma unroll 1
       for (int b = 0; b < kMB; b += kFB) {
+        if (Cfg::SYNC == 1) asm volatile("bar.sync %0, %1;" ::"r"(1 + (warp & 3)), "r"(32 * (kNW / 4)) : "memory");
         if (Cfg::FLUSH == 0 && Cfg::DIAG != 1) {
           float accb[kR];                    // partial sums of this flush interval only
 #pragma unroll
@@ -390,7 +405,9 @@ ct_finalize_kernel(const double* __restrict__ S, int nC, int nF, int nR, int L, 
 // C ABI
 // ================================================================================================
 // The product launches kLong for long chunks and kShort (smaller lag / frame tiles) for short ones.
-using CtLong = CtCfg<19, 12, 3, 12, 1, 2>;     // R = 19, 12 warps, 1 CTA/SM, 2 stages of 2736 frames: 57 terms per FP32 partial sum
+// R = 19, 12 warps, 1 CTA/SM, 2 stages of 2736 frames, 57 terms per FP32 partial sum, and the three warps of every SM
+// sub-partition re-aligned at a named barrier once per step (SYNC = 2): +7 % (tools/tune_ct.py, profiles/r02l_tune_ct.json)
+using CtLong = CtCfg<19, 12, 3, 12, 1, 2, 0, 0, 0, 2>;
 using CtShort = CtCfg<15, 8, 1, 8, 2, 3>;      // R = 15, 8 warps, 2 CTAs/SM, 3 stages: 15 terms per FP32 partial sum (few chunk
                                                // means enter dCt when chunks are short, so keep its rounding at the 1e-7 level)
 constexpr long long kShortFrames = 8192;
