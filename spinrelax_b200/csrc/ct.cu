@@ -91,6 +91,8 @@ __device__ __forceinline__ void ct_block(const float* __restrict__ LX, const flo
     const int iw = s + kk + o + kR;                                              // frame entering the window
     if (Cfg::DIAG == 2 || Cfg::DIAG == 4) { nx = wx[kk] + 1e-7f; ny = wy[kk]; nz = wz[kk]; }
     else { nx = WX[iw]; ny = WY[iw]; nz = WZ[iw]; }
+    if (Cfg::SYNC == 12)   // re-align after the step's loads have been issued
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + (int)((threadIdx.x >> 5) & 3)), "r"(32 * (Cfg::NW / 4)));
     if (DOFLUSH && Cfg::DIAG != 1) {
       if (Cfg::FLUSH == 1) acc64[kk] += (double)acc[kk];
       if (Cfg::FLUSH == 2) sacc[o + kk] += (double)acc[kk];
@@ -118,7 +120,7 @@ __device__ __forceinline__ void ct_block(const float* __restrict__ LX, const flo
 #pragma unroll
         for (int j = 0; j < kR; ++j) d[j] = fmaf(az, wz[(kk + j) % kR], d[j]);
 #pragma unroll
-        for (int j = 0; j < kR; ++j) acc[j] = fmaf(d[j], d[j], acc[j]);
+        for (int j = 0; j < kR; ++j) acc[j] = (DOFLUSH && j == kk) ? d[j] * d[j] : fmaf(d[j], d[j], acc[j]);
       } else {
 #pragma unroll
         for (int j = 0; j < kR; ++j) asm volatile("mul.rn.f32 %0, %1, %2;" : "=f"(d[j]) : "f"(ax), "f"(wx[(kk + j) % kR]));
@@ -127,7 +129,10 @@ __device__ __forceinline__ void ct_block(const float* __restrict__ LX, const flo
 #pragma unroll
         for (int j = 0; j < kR; ++j) asm volatile("fma.rn.f32 %0, %1, %2, %0;" : "+f"(d[j]) : "f"(az), "f"(wz[(kk + j) % kR]));
 #pragma unroll
-        for (int j = 0; j < kR; ++j) asm volatile("fma.rn.f32 %0, %1, %1, %0;" : "+f"(acc[j]) : "f"(d[j]));
+        for (int j = 0; j < kR; ++j) {
+          if (DOFLUSH && j == kk) acc[j] = d[j] * d[j];
+          else asm volatile("fma.rn.f32 %0, %1, %1, %0;" : "+f"(acc[j]) : "f"(d[j]));
+        }
       }
     }
     wx[kk] = nx; wy[kk] = ny; wz[kk] = nz;
@@ -405,16 +410,19 @@ ct_finalize_kernel(const double* __restrict__ S, int nC, int nF, int nR, int L, 
 // C ABI
 // ================================================================================================
 // The product launches kLong for long chunks and kShort (smaller lag / frame tiles) for short ones.
-// R = 19, 12 warps, 1 CTA/SM, 2 stages of 2736 frames, 57 terms per FP32 partial sum, and the three warps of every SM
-// sub-partition re-aligned at a named barrier once per step (SYNC = 2): +7 % (tools/tune_ct.py, profiles/r02l_tune_ct.json)
-using CtLong = CtCfg<19, 12, 3, 12, 1, 2, 0, 0, 0, 2>;
+// R = 23 lags per lane, 12 warps, 1 CTA/SM, 2 stages of 2484 frames, 69 terms per FP32 partial sum, and the three warps
+// of every SM sub-partition re-aligned at a named barrier once per step (SYNC = 2).  Round 1 shipped R = 19 without
+// the barrier (0.613 of peak on the tuning slice); the barrier alone gives 0.658, and only with it does a wider window
+// pay (R = 21: 0.667, R = 23: 0.686, R = 25 / 27 / 29: 0.672 / 0.680 (sums in shared memory) / 0.644 -- the loop body
+// outgrows 32 KB of instruction cache).  tools/tune_ct.py, profiles/r02l..r02p_tune_ct.json.
+using CtLong = CtCfg<23, 9, 3, 12, 1, 2, 0, 0, 0, 2>;
 using CtShort = CtCfg<15, 8, 1, 8, 2, 3>;      // R = 15, 8 warps, 2 CTAs/SM, 3 stages: 15 terms per FP32 partial sum (few chunk
                                                // means enter dCt when chunks are short, so keep its rounding at the 1e-7 level)
 constexpr long long kShortFrames = 8192;
 #ifdef SR_TUNING
 constexpr int kMaxTF = 2736, kMaxTL = 32 * 45;
 #else
-constexpr int kMaxTF = 2736, kMaxTL = 32 * 19;   // padding must cover the largest tile of any configuration
+constexpr int kMaxTF = 2736, kMaxTL = 32 * 23;   // padding must cover the largest tile of any configuration
 #endif
 
 template <class Cfg>
