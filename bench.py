@@ -206,6 +206,9 @@ def run_reference(args):
     value = pairs * len(times) / total
     sample = ("oracle port of the per-lag body (calculate-Ct-from-traj.py:223-228) on the full config-2 array, "
               "%d lags spread over 1..1e5 x 4 vector blocks per step, %d worker processes" % (len(lags), cores))
+    if args.gpus > 1:
+        sample += ("; the config-4 job is the same loop body over 2000 instead of 76 vectors (cost per pair identical), "
+                   "sampled here on the 76 seeded base trajectories the config-4 set is built from")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
