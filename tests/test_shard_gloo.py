@@ -83,3 +83,18 @@ def test_partition_properties():
             assert np.array_equal(got, lags)
     v = np.zeros((2, 10, 7, 3))
     assert shard.shard_vectors(v, 2, 0).shape == (2, 10, 4, 3) and shard.shard_vectors(v, 2, 1).shape == (2, 10, 3, 3)
+
+
+def test_multigpu_plan_partitions_units_over_selected_devices(monkeypatch):
+    """Single-process multi-device sharding (spinrelax_b200.multigpu): contiguous balanced blocks, a minimum block size,
+    and never more blocks than devices -- checked without a GPU by faking the device list."""
+    from spinrelax_b200 import multigpu
+    monkeypatch.setattr(multigpu, "devices", lambda: [0, 1, 2, 3, 4, 5, 6, 7])
+    blocks = multigpu.plan(2000)
+    assert [d for d, _, _ in blocks] == list(range(8)) and blocks[0][1] == 0 and blocks[-1][2] == 2000
+    assert all(blocks[i][2] == blocks[i + 1][1] for i in range(7)) and {b - a for _, a, b in blocks} == {250}
+    assert [(a, b) for _, a, b in multigpu.plan(7)] == [(0, 1)] * 0 + [(i, i + 1) for i in range(7)]      # fewer units than devices
+    assert len(multigpu.plan(100, min_per_device=32)) == 3                                              # 34 + 33 + 33
+    assert multigpu.plan(10, min_per_device=32) == [(0, 0, 10)]
+    monkeypatch.setattr(multigpu, "devices", lambda: [3])
+    assert multigpu.plan(76) == [(3, 0, 76)]
