@@ -410,12 +410,15 @@ ct_finalize_kernel(const double* __restrict__ S, int nC, int nF, int nR, int L, 
 // C ABI
 // ================================================================================================
 // The product launches kLong for long chunks and kShort (smaller lag / frame tiles) for short ones.
-// R = 23 lags per lane, 12 warps, 1 CTA/SM, 2 stages of 2484 frames, 69 terms per FP32 partial sum, and the three warps
-// of every SM sub-partition re-aligned at a named barrier once per step (SYNC = 2).  Round 1 shipped R = 19 without
-// the barrier (0.613 of peak on the tuning slice); the barrier alone gives 0.658, and only with it does a wider window
-// pay (R = 21: 0.667, R = 23: 0.686, R = 25 / 27 / 29: 0.672 / 0.680 (sums in shared memory) / 0.644 -- the loop body
-// outgrows 32 KB of instruction cache).  tools/tune_ct.py, profiles/r02l..r02p_tune_ct.json.
-using CtLong = CtCfg<23, 9, 3, 12, 1, 2, 0, 0, 0, 2>;
+// R = 23 lags per lane, 12 warps, 1 CTA/SM, 2 stages of 2484 frames; the three warps of every SM sub-partition
+// re-aligned at a named barrier once per step (SYNC = 2); the four FMA-pipe instructions of a step issued in phases
+// (ORDER = 1); FP64 lag sums in shared memory, flushed once per warp tile (FLUSH = 2, FB = MB: 207 terms per FP32 partial
+// sum, S within 4e-8 of the float64 oracle).  Round 1 shipped R = 19 without the barrier, sums in registers flushed every
+// 57 terms: 0.613 of peak on the tuning slice.  Barrier alone 0.658; R = 23 0.686-0.688; phased order 0.693; sums in
+// shared memory (no spills) 0.697; flushing them once per tile instead of three times 0.7256.  Wider windows lose again
+// (R = 25: 0.713, R = 27: 0.668: the loop body outgrows 32 KB of instruction cache).
+// tools/tune_ct.py, profiles/r02l..r02y_tune_ct.json.
+using CtLong = CtCfg<23, 9, 9, 12, 1, 2, 2, 0, 1, 2>;
 using CtShort = CtCfg<15, 8, 1, 8, 2, 3>;      // R = 15, 8 warps, 2 CTAs/SM, 3 stages: 15 terms per FP32 partial sum (few chunk
                                                // means enter dCt when chunks are short, so keep its rounding at the 1e-7 level)
 constexpr long long kShortFrames = 8192;

@@ -160,7 +160,7 @@ class CtHistStep:
         return n
 
     # tile configuration of the ct_lag_kernel instantiation the library launches for long chunks (csrc/ct.cu: CtLong)
-    CT_LAG_CONFIG = "CtCfg<R=23,MB=9,FB=3,NW=12,MINB=1,NS=2,FLUSH=0,SYNC=2>"
+    CT_LAG_CONFIG = "CtCfg<R=23,MB=9,FB=9,NW=12,MINB=1,NS=2,FLUSH=2,ORDER=1,SYNC=2>"
 
     @classmethod
     def ncu_traffic_bytes(cls):

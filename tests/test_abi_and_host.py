@@ -417,9 +417,9 @@ def test_ncu_traffic_record_is_tied_to_the_shipped_tile_configuration():
     from conftest import ROOT
     from spinrelax_b200 import pipeline
     src = open(os.path.join(ROOT, "spinrelax_b200", "csrc", "ct.cu")).read()
-    m = re.search(r"using CtLong = CtCfg<(\d+), (\d+), (\d+), (\d+), (\d+), (\d+), (\d+), 0, 0, (\d+)>;", src)
+    m = re.search(r"using CtLong = CtCfg<(\d+), (\d+), (\d+), (\d+), (\d+), (\d+), (\d+), 0, (\d+), (\d+)>;", src)
     assert m, "CtLong not found"
-    tag = "CtCfg<R=%s,MB=%s,FB=%s,NW=%s,MINB=%s,NS=%s,FLUSH=%s,SYNC=%s>" % m.groups()
+    tag = "CtCfg<R=%s,MB=%s,FB=%s,NW=%s,MINB=%s,NS=%s,FLUSH=%s,ORDER=%s,SYNC=%s>" % m.groups()
     assert pipeline.CtHistStep.CT_LAG_CONFIG == tag
     rec = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
     assert (pipeline.CtHistStep.ncu_traffic_bytes() is not None) == (rec.get("kernel_config") == tag)
