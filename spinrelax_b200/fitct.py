@@ -530,15 +530,15 @@ class autoCorrelations:
             Cs, taus = take(C), take(tau)
             dCs, dtaus = take(dParam[:, :nc]), take(dParam[:, nc:2 * nc])
             dS2 = dParam[:, -1] if fast else np.zeros(a.size)
-            for j, i in enumerate(a):
-                if finite[j]:
-                    if not q_over[j]:
-                        lines.append("= = = WARNING, curve fitting of %s with %i params indicates overfitting." % (names[i], nParams))
-                    if not q_sum[j]:
-                        lines.append("= = = WARNING, curve fitting of %s with %i params returns sum>1." % (names[i], nParams))
-                else:
+            for i, fin, qo, qs, c in zip(a.tolist(), finite.tolist(), q_over.tolist(), q_sum.tolist(), chi.tolist()):
+                if not fin:
                     lines.append("= = = WARNING, curve fitting of %s with %i params failed!" % (names[i], nParams))
-                lines.append("    ...%s: fit with %i params yield chiSq of %g" % (names[i], nParams, chi[j]))
+                else:
+                    if not qo:
+                        lines.append("= = = WARNING, curve fitting of %s with %i params indicates overfitting." % (names[i], nParams))
+                    if not qs:
+                        lines.append("= = = WARNING, curve fitting of %s with %i params returns sum>1." % (names[i], nParams))
+                lines.append("    ...%s: fit with %i params yield chiSq of %g" % (names[i], nParams, c))
             # selection ladder (optimised_curve_fitting :288-304)
             was_first = first[a]
             accept = np.where(was_first, ok, ok & ~(chi >= best["chi"][a] * chiSqThreshold))
