@@ -23,7 +23,7 @@ namespace {
 // frame per step (static circular indexing, fully unrolled over R), so one step costs
 // 6 LDS.32 + 4R FMA-pipe instructions.
 // ------------------------------------------------------------------------------------------------
-// Tile geometry is a compile-time configuration; kLong / kShort are what the product launches.  Building with
+// Tile geometry is a compile-time configuration; CtLong / CtShort are what the product launches.  Building with
 // -DSR_TUNING (tools/build_tune.py -> tools/libct_tune.so, never the product library) adds the table of experimental
 // configurations and the entry point sr_ct_lag_sums_variant that tools/tune_ct.py times on the GPU.
 //
@@ -409,7 +409,7 @@ ct_finalize_kernel(const double* __restrict__ S, int nC, int nF, int nR, int L, 
 // ================================================================================================
 // C ABI
 // ================================================================================================
-// The product launches kLong for long chunks and kShort (smaller lag / frame tiles) for short ones.
+// The product launches CtLong for long chunks and CtShort (smaller lag / frame tiles) for short ones.
 // R = 23 lags per lane, 12 warps, 1 CTA/SM, 2 stages of 2484 frames; the three warps of every SM sub-partition
 // re-aligned at a named barrier once per step (SYNC = 2); the four FMA-pipe instructions of a step issued in phases
 // (ORDER = 1); FP64 lag sums in shared memory, flushed once per warp tile (FLUSH = 2, FB = MB: 207 terms per FP32 partial
