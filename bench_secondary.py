@@ -110,8 +110,8 @@ def synth_curves(n_res, n_pts, seed):
 
 def bench_fit_relax(quick, emit=True):
     import torch
-    from oracle import ct_oracle, fit_oracle, sd_oracle
-    from spinrelax_b200 import fitct, specdens as sd, synth
+    from oracle import fit_oracle, sd_oracle                    # cpu_baseline legs only
+    from spinrelax_b200 import fitct, hist as sr_hist, specdens as sd, synth
     nR = 200 if quick else 1000
     t, Y, SG = synth_curves(nR, 500, 77)
     ac = fitct.autoCorrelations()
@@ -142,7 +142,7 @@ def bench_fit_relax(quick, emit=True):
     # relaxation grid: histogram weights from a synthetic rotated stream, 5 fields x 64 CSA values
     q = np.array([0.8, -0.36, 0.48, 0.0])
     v = synth.nh_vectors(2000, nR, seed=5)
-    hist, edges = ct_oracle.sphere_histogram(v, q)              # input preparation only (not timed)
+    hist, edges = sr_hist.sphere_histogram(v, q)                # input preparation (not timed): the product's K3
     vecs, w = sd.convert_LambertCylindricalHist_to_vecs(hist, edges)
     rot = sd.globalRotationalDiffusion_Axisymmetric(D=[2.1e-5, 1.35])
     rot.set_frame_vectors(np.arange(nR), vecs, w)
