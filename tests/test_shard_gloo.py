@@ -98,3 +98,72 @@ def test_multigpu_plan_partitions_units_over_selected_devices(monkeypatch):
     assert multigpu.plan(10, min_per_device=32) == [(0, 0, 10)]
     monkeypatch.setattr(multigpu, "devices", lambda: [3])
     assert multigpu.plan(76) == [(3, 0, 76)]
+
+
+def _oracle_worker(rank, world, port, out_dir):
+    """Each rank runs the oracle on its share (the stand-in for the device stage) and the product's shard helpers move
+    the results: what rank 0 ends up with must be what the unsharded oracle produces."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from oracle import ct_oracle, dq_oracle
+    from spinrelax_b200 import synth
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        nC, nF, nR = 3, 200, 7                       # 7 vectors over 2 ranks: shares of 4 and 3
+        v4 = synth.nh_vectors(nC * nF, nR, seed=11).reshape(nC, nF, nR, 3)
+        q_rot = np.array([0.83, -0.31, 0.22, 0.41])
+        a, b = shard.split_range(nR, world, rank)
+        Ct, dCt = ct_oracle.ct_palmer(v4[:, :, a:b])
+        both = torch.from_numpy(np.concatenate((Ct, dCt), axis=0))
+        full = shard.gather_columns(both, nR, dst=0)
+        h, _ = ct_oracle.sphere_histogram(v4[:, :, a:b].reshape(nC * nF, b - a, 3), q_rot)
+        hall = shard.gather_rows(torch.from_numpy(h.astype(np.int64)), nR, dst=0)
+        # the same histogram sharded by frames instead: one all-reduce of the counts
+        fa, fb = shard.split_range(nC * nF, world, rank)
+        hf, _ = ct_oracle.sphere_histogram(v4.reshape(nC * nF, nR, 3)[fa:fb], q_rot)
+        hf = torch.from_numpy(hf.astype(np.int64))
+        shard.allreduce_sum_(hf)
+        # dq second moments: lags round-robin over the ranks (every rank holds the trajectory) ...
+        q = synth.quaternion_walk(600, seed=5, sigma=(0.01, 0.015, 0.03))
+        lags = np.arange(2, 40, 3)
+        mine = shard.shard_lags(lags, world, rank)
+        rows = np.array([np.concatenate(([dq_oracle.iso_moment_shipped(dq_oracle.self_dq(q, int(d))[..., 1:4])],
+                                        dq_oracle.aniso_tensor(dq_oracle.self_dq(q, int(d))[..., 1:4]).ravel())) for d in mine])
+        merged = shard.merge_lag_results(torch.from_numpy(rows), lags, world, dst=0)
+        # ... and replica pooling (calculate-dq-distribution-multi.py:529-540): one trajectory per rank, raw sums all-reduced
+        qr = synth.quaternion_walk(600, seed=20 + rank, sigma=(0.01, 0.015, 0.03))
+        vq = dq_oracle.self_dq(qr, 5)[..., 1:4]
+        sums = torch.from_numpy(np.concatenate(((vq[:, :, None] * vq[:, None, :]).sum(axis=0).ravel(), [len(vq)])))
+        shard.allreduce_sum_(sums)
+        if rank == 0:
+            np.savez(os.path.join(out_dir, "o0.npz"), full=full.numpy(), hall=hall.numpy(), hf=hf.numpy(),
+                     merged=merged.numpy(), pooled=sums.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_sharded_stages_equal_the_unsharded_oracle(tmp_path):
+    """Bond vectors are independent (calculate-Ct-from-traj.py:222-228), histograms add over frames, lags are independent
+    and replicas pool their samples: the sharded data flow of every stage reproduces the one-process result."""
+    from oracle import ct_oracle, dq_oracle
+    from spinrelax_b200 import synth
+    world = 2
+    mp.spawn(_oracle_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    r = np.load(tmp_path / "o0.npz")
+    nC, nF, nR = 3, 200, 7
+    v4 = synth.nh_vectors(nC * nF, nR, seed=11).reshape(nC, nF, nR, 3)
+    q_rot = np.array([0.83, -0.31, 0.22, 0.41])
+    Ct, dCt = ct_oracle.ct_palmer(v4)
+    assert np.array_equal(r["full"], np.concatenate((Ct, dCt), axis=0))
+    h, _ = ct_oracle.sphere_histogram(v4.reshape(nC * nF, nR, 3), q_rot)
+    assert np.array_equal(r["hall"], h.astype(np.int64)) and np.array_equal(r["hf"], h.astype(np.int64))
+    q = synth.quaternion_walk(600, seed=5, sigma=(0.01, 0.015, 0.03))
+    lags = np.arange(2, 40, 3)
+    for row, d in zip(r["merged"], lags):
+        vq = dq_oracle.self_dq(q, int(d))[..., 1:4]
+        assert row[0] == dq_oracle.iso_moment_shipped(vq) and np.array_equal(row[1:], dq_oracle.aniso_tensor(vq).ravel())
+    pooled = dq_oracle.pooled_vectors([synth.quaternion_walk(600, seed=20 + k, sigma=(0.01, 0.015, 0.03)) for k in range(world)], 5)
+    assert r["pooled"][-1] == len(pooled)
+    np.testing.assert_allclose(r["pooled"][:9] / r["pooled"][-1], dq_oracle.aniso_tensor(pooled).ravel(), rtol=1e-13, atol=1e-18)
