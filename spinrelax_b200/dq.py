@@ -148,7 +148,9 @@ def _rotated_batch(M, qframe):
     if qs.nearly_identity(qframe):
         return M
     R = qs.rotation_matrix(qframe)
-    return R @ M @ R.T
+    # vec(R M R^T) = (R kron R) vec(M), row-major: one (n, 9) x (9, 9) product instead of 2n tiny 3x3 ones
+    M = np.asarray(M, dtype=float)
+    return (M.reshape(-1, 9) @ np.kron(R, R).T).reshape(M.shape)
 
 
 def _rotated(M33, qframe):
